@@ -1,0 +1,32 @@
+/* loraine_b200 -- test / benchmark hooks onto the library's dense primitives (not part of the drop-in boundary).
+ * All pointers are HOST pointers (column-major, leading dimension = rows); the hooks stage through device memory
+ * with the library's padded leading dimensions so that the tests exercise the same code paths as the solver. */
+#ifndef LORAINE_B200_DEBUG_H
+#define LORAINE_B200_DEBUG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* C = alpha*op(A)*op(B)[.*colscale] + beta*C (mode 0) or C = beta*C + alpha*(op(A)op(B)).^2 (mode 1); lower != 0 computes
+ * only tiles that intersect the lower triangle.  misalign != 0 offsets the device buffers by 8 bytes (exercises the
+ * unaligned cp.async path).  reps > 0: the kernel is timed over `reps` launches (CUDA events) into *ms_per_launch. */
+int32_t lrn_dbg_gemm(int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, double alpha, const double* A,
+                     const double* B, double beta, double* C, int32_t mode, int32_t lower, const double* colscale,
+                     int32_t misalign, int32_t reps, double* ms_per_launch);
+/* A (n x n, symmetric, lower used) -> L in the lower triangle (upper zeroed); x (n) <- solve per `which` (0 = skip) */
+int32_t lrn_dbg_cholesky(int32_t n, double* A, double* x, int32_t which, int32_t* info, int32_t reps, double* ms_factor);
+/* symmetric n <= 64: eigenvalues (descending) and eigenvectors */
+int32_t lrn_dbg_eig_small(int32_t n, const double* A, double* evals, double* V, int32_t relative);
+/* one-sided block Jacobi SVD of the m x m matrix A: UD = U*diag(sigma), V, sigma (descending) */
+int32_t lrn_dbg_svd(int32_t m, const double* A, double* UD, double* V, double* sigma, double tol, int32_t* sweeps, double* ms);
+/* Lanczos extreme eigenpairs of the symmetric m x m matrix T */
+int32_t lrn_dbg_lanczos(int32_t m, const double* T, int32_t nev_top, double tol, double* lmin, double* lmax,
+                        double* top_vals, double* top_vecs, int32_t* iters, int32_t* converged);
+/* device micro-benchmarks: kind 0 = DMMA (mma.sync m8n8k4 f64) register-resident peak, 1 = DFMA peak, 2 = HBM copy GB/s */
+int32_t lrn_dbg_peak(int32_t kind, double* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

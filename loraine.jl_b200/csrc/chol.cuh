@@ -1,0 +1,34 @@
+// Dense blocked FP64 Cholesky (lower) + blocked triangular solves.
+// Replaces LAPACK dpotrf/dtrsv behind `cholesky(Hermitian(BBBB,:L))` and `L' \ (L \ h)` (src/predictor_corrector.jl:57,89-90,199)
+// and behind `cholesky(X[i])` / `cholesky(S[i])` (src/prepare_W.jl:7,24), `cholesky(S)` (src/Solvers.jl:805).
+#pragma once
+#include "common.cuh"
+
+namespace lrn {
+
+constexpr int CHOL_DB = 64;   // diagonal block size (one CTA, shared memory)
+
+// Workspace: inverses of the 64x64 diagonal blocks of L (used by the panel TRSM and by the triangular solves).
+struct CholWork {
+    DevBuf<double> dinv;      // cdiv(n,64) blocks of 64x64 (ld 64), zero above the diagonal
+    DevBuf<int> info;         // [0] = 0 ok, >0 = 1-based index of the first non-positive pivot (LAPACK convention)
+    int* info_ext = nullptr;  // optional external flag location (lets the caller gather many flags with one copy)
+    int n = 0;
+    void ensure(int n_) {
+        if (n_ > n || !dinv.p) { dinv.alloc((size_t)cdiv(n_, CHOL_DB) * CHOL_DB * CHOL_DB); n = n_; }
+        if (!info.p) info.alloc(1);
+    }
+    int* info_ptr() const { return info_ext ? info_ext : info.p; }
+};
+
+// Factor the lower triangle of A (n x n, column-major, lda) in place: A = L L^T. The strict upper triangle is ignored
+// (inside diagonal 128-tiles it may be overwritten with don't-care values). Enqueues only; read `work.info` after a sync.
+void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st);
+
+// x <- L^{-1} x (which=1), x <- L^{-T} x (which=2), both (which=3). `tmp` has n doubles. Uses work.dinv of the same factor.
+void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st);
+
+// Zero the strict upper triangle (so the factor can be used as a dense GEMM operand).
+void zero_strict_upper(double* A, int n, int lda, cudaStream_t st);
+
+}  // namespace lrn

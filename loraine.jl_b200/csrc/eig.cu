@@ -1,0 +1,589 @@
+#include "eig.cuh"
+#include "gemm.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace lrn {
+namespace {
+
+constexpr int EN = 64, ELD = 65;
+constexpr size_t EIG_SMEM = (2 * EN * ELD + 64) * sizeof(double) + 64 * sizeof(int);
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    // valid for non-negative finite doubles: bit patterns are ordered like unsigned integers
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// Batched two-sided cyclic Jacobi with round-robin parallel ordering, everything in shared memory.
+__global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams P) {
+    extern __shared__ double sm[];
+    double* a = sm;
+    double* v = sm + EN * ELD;
+    double* cs = v + EN * ELD;      // 32
+    double* sn = cs + 32;           // 32
+    int* pp = reinterpret_cast<int*>(sn + 32);
+    int* qq = pp + 32;
+    __shared__ int rotated;
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x, z = blockIdx.x;
+    const int n = P.n, n2 = (n + 1) & ~1, h = n2 >> 1;
+    const double* Az = P.A + (size_t)z * P.sA;
+
+    for (int idx = tid; idx < EN * EN; idx += 256) {
+        int i = idx % EN, j = idx / EN;
+        double val = 0.0;
+        if (i < n && j < n)
+            for (int t = 0; t < P.nparts; t++) val += Az[(size_t)t * P.sPart + (size_t)j * P.lda + i];
+        a[i * ELD + j] = val;
+        v[i * ELD + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < EN * EN; idx += 256) {
+        int i = idx % EN, j = idx / EN;
+        if (i > j) {
+            double t = 0.5 * (a[i * ELD + j] + a[j * ELD + i]);
+            a[i * ELD + j] = t;
+            a[j * ELD + i] = t;
+        }
+    }
+    __syncthreads();
+    double lsum = 0.0, lmax = 0.0;
+    for (int idx = tid; idx < EN * EN; idx += 256) {
+        int i = idx % EN, j = idx / EN;
+        double x = a[i * ELD + j];
+        lsum += x * x;
+        if (i < j && x != 0.0) {
+            double den = sqrt(fabs(a[i * ELD + i] * a[j * ELD + j]));
+            double r = (den > 0.0) ? fabs(x) / den : 1.0e300;
+            lmax = fmax(lmax, r);
+        }
+    }
+    const double fro = sqrt(block_sum(lsum, red));
+    if (P.offmax) {
+        lmax = warp_max(lmax);
+        if ((tid & 31) == 0) atomic_max_nonneg(P.offmax, fmin(lmax, 1.0e300));
+    }
+    const double abs_tol = P.relative ? 0.0 : 1.0e-18 * fro;
+    const double rel_tol = 1.0e-15;
+
+    for (int sweep = 0; sweep < 40; sweep++) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int r = 0; r < n2 - 1; r++) {
+            if (tid < h) {
+                int p, q;
+                if (tid == 0) { p = n2 - 1; q = r; }
+                else { p = (r + tid) % (n2 - 1); q = (r - tid + (n2 - 1)) % (n2 - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < n) {
+                    double apq = a[p * ELD + q], app = a[p * ELD + p], aqq = a[q * ELD + q];
+                    double thr = fmax(rel_tol * sqrt(fabs(app * aqq)), abs_tol);
+                    if (fabs(apq) > thr) {
+                        double theta = (aqq - app) / (2.0 * apq);
+                        double t;
+                        if (fabs(theta) > 1.0e100) t = 0.5 / theta;
+                        else t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = rsqrt(t * t + 1.0);
+                        s = t * c;
+                        rotated = 1;
+                    }
+                }
+                cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+            }
+            __syncthreads();
+            for (int item = tid; item < h * n2; item += 256) {     // rows p,q  <-  J^T A
+                int k = item / n2, j = item - k * n2;
+                double s = sn[k];
+                if (s != 0.0) {
+                    double c = cs[k];
+                    int p = pp[k], q = qq[k];
+                    double ap = a[p * ELD + j], aq = a[q * ELD + j];
+                    a[p * ELD + j] = c * ap - s * aq;
+                    a[q * ELD + j] = s * ap + c * aq;
+                }
+            }
+            __syncthreads();
+            for (int item = tid; item < h * n2; item += 256) {     // cols p,q  <-  A J ;  V J
+                int k = item / n2, i = item - k * n2;
+                double s = sn[k];
+                if (s != 0.0) {
+                    double c = cs[k];
+                    int p = pp[k], q = qq[k];
+                    double ap = a[i * ELD + p], aq = a[i * ELD + q];
+                    a[i * ELD + p] = c * ap - s * aq;
+                    a[i * ELD + q] = s * ap + c * aq;
+                    double vp = v[i * ELD + p], vq = v[i * ELD + q];
+                    v[i * ELD + p] = c * vp - s * vq;
+                    v[i * ELD + q] = s * vp + c * vq;
+                }
+            }
+            __syncthreads();
+            if (tid < h && sn[tid] != 0.0) {
+                int p = pp[tid], q = qq[tid];
+                a[p * ELD + q] = 0.0;
+                a[q * ELD + p] = 0.0;
+            }
+            __syncthreads();
+        }
+        const int any_rot = rotated;
+        __syncthreads();           // everyone has read the flag before thread 0 may reset it
+        if (!any_rot) break;
+    }
+
+    // output (optionally sorted descending by eigenvalue; ties broken by index)
+    if (tid < n) {
+        double li = a[tid * ELD + tid];
+        int rank = tid;
+        if (P.sort_desc) {
+            rank = 0;
+            for (int j = 0; j < n; j++) {
+                double lj = a[j * ELD + j];
+                if (lj > li || (lj == li && j < tid)) rank++;
+            }
+        }
+        pp[tid] = rank;     // pairs finished: reuse as rank table (n <= 64 needs 64 ints: pp+qq are contiguous)
+        if (P.evals) P.evals[(size_t)z * P.sE + rank] = li;
+    }
+    if (P.minval) {
+        double li = (tid < n) ? a[tid * ELD + tid] : 1.0e300;
+        li = warp_min(li);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = li;
+        __syncthreads();
+        if (tid == 0) {
+            double m = red[0];
+            for (int w = 1; w < 8; w++) m = fmin(m, red[w]);
+            P.minval[z] = m;
+        }
+    }
+    __syncthreads();
+    if (P.V) {
+        double* Vz = P.V + (size_t)z * P.sV;
+        for (int idx = tid; idx < n * n; idx += 256) {
+            int i = idx % n, j = idx / n;
+            Vz[(size_t)pp[j] * P.ldv + i] = v[i * ELD + j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one-sided block Jacobi helpers
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void svd_init_kernel(const double* __restrict__ A, int lda, int m, int mp, double* __restrict__ W, int ldw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;    // row in stacked buffer
+    int j = blockIdx.y;                               // column
+    if (i >= m + mp) return;
+    double v;
+    if (i < m) v = (j < m) ? A[(size_t)j * lda + i] : 0.0;
+    else v = (i - m == j) ? 1.0 : 0.0;
+    W[(size_t)j * ldw + i] = v;
+}
+
+__global__ void __launch_bounds__(256) colnorm_kernel(const double* __restrict__ W, int ldw, int m, int ncols, double* __restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ncols) return;
+    const double* c = W + (size_t)warp * ldw;
+    // scaled two-pass not needed: entries are O(sigma), squares stay in range for IPM data
+    double s = 0.0;
+    for (int i = lane; i < m; i += 32) s += c[i] * c[i];
+    s = warp_sum(s);
+    if (lane == 0) out[warp] = sqrt(s);
+}
+
+__global__ void rank_desc_kernel(const double* __restrict__ v, int n, int* __restrict__ perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double vi = v[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        double vj = v[j];
+        if (vj > vi || (vj == vi && j < i)) rank++;
+    }
+    perm[rank] = i;
+}
+
+__global__ void svd_gather_kernel(const double* __restrict__ W, int ldw, int m, const int* __restrict__ perm,
+                                  const double* __restrict__ sv, double* __restrict__ UD, int ldu, double* __restrict__ V,
+                                  int ldv, double* __restrict__ sigma) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    int src = perm[r];
+    if (i < m) {
+        UD[(size_t)r * ldu + i] = W[(size_t)src * ldw + i];
+        V[(size_t)r * ldv + i] = W[(size_t)src * ldw + m + i];
+    }
+    if (i == 0) sigma[r] = sv[src];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lanczos kernels
+// ---------------------------------------------------------------------------------------------------------------
+// y[c] = sum_i A[i + c*ld] * x[i]   (one warp per column; for symmetric A this is A*x with fully coalesced reads)
+__global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ A, int ld, int rows, int cols,
+                                                     const double* __restrict__ x, double* __restrict__ y) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= cols) return;
+    const double* c = A + (size_t)warp * ld;
+    double s = 0.0;
+    for (int i = lane; i < rows; i += 32) s += c[i] * x[i];
+    s = warp_sum(s);
+    if (lane == 0) y[warp] = s;
+}
+// w[i] -= sum_k Q[i + k*ld] * c[k]
+__global__ void __launch_bounds__(256) gemv_n_sub_kernel(const double* __restrict__ Q, int ld, int rows, int cols,
+                                                         const double* __restrict__ c, double* __restrict__ w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    double s = 0.0;
+    for (int k = 0; k < cols; k++) s += Q[(size_t)k * ld + i] * c[k];
+    w[i] -= s;
+}
+__global__ void __launch_bounds__(1024) lanczos_init_kernel(double* __restrict__ q, int m) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < m; i += 1024) {
+        unsigned hsh = (unsigned)i * 2654435761u + 12345u;
+        hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+        double x = 0.5 + (double)(hsh & 0xffffu) / 65536.0;     // in [0.5, 1.5): never orthogonal to a Perron-like vector
+        if (hsh & 0x10000u) x = -x;
+        q[i] = x;
+        s += x * x;
+    }
+    s = block_sum(s, red);
+    double inv = rsqrt(s);
+    for (int i = threadIdx.x; i < m; i += 1024) q[i] *= inv;
+}
+// alpha = q_j . w ; w -= alpha*q_j + beta_prev*q_{j-1}
+__global__ void __launch_bounds__(1024) lanczos_alpha_kernel(double* __restrict__ w, const double* __restrict__ qj,
+                                                             const double* __restrict__ qjm1, double beta_prev, int m,
+                                                             double* __restrict__ scal) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < m; i += 1024) s += qj[i] * w[i];
+    double alpha = block_sum(s, red);
+    for (int i = threadIdx.x; i < m; i += 1024) {
+        double x = w[i] - alpha * qj[i];
+        if (qjm1) x -= beta_prev * qjm1[i];
+        w[i] = x;
+    }
+    if (threadIdx.x == 0) scal[0] = alpha;
+}
+// beta = ||w|| ; q_next = w / beta
+__global__ void __launch_bounds__(1024) lanczos_beta_kernel(const double* __restrict__ w, double* __restrict__ qn, int m,
+                                                            double* __restrict__ scal) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < m; i += 1024) s += w[i] * w[i];
+    double beta = sqrt(block_sum(s, red));
+    double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+    for (int i = threadIdx.x; i < m; i += 1024) qn[i] = w[i] * inv;
+    if (threadIdx.x == 0) scal[1] = beta;
+}
+
+}  // namespace
+
+void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st) {
+    LRN_REQUIRE(p.n >= 1 && p.n <= EN, "jacobi_eig_small handles n <= 64");
+    static bool configured = false;
+    if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(jacobi_eig64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
+        configured = true;
+    }
+    jacobi_eig64_kernel<<<p.batch, 256, EIG_SMEM, st>>>(p);
+    LRN_CHECK_LAUNCH();
+}
+
+void SvdWork::ensure(int m_) {
+    if (m_ == m && buf0.p) return;
+    m = m_;
+    mp = round_up(m, 64);
+    ldw = pad_ld(m + mp);
+    size_t elems = (size_t)ldw * mp;
+    buf0.alloc(elems);
+    buf1.alloc(elems);
+    const int nblk = mp / 32, pairs = nblk / 2;
+    splits = (int)std::min<long long>(8, std::max<long long>(1, 148 / pairs));
+    Kc = round_up((int)cdiv(m, splits), 16);
+    if (Kc < 64) Kc = 64;
+    splits = (int)cdiv(m, Kc);
+    if (splits == 1) Kc = m;
+    gram.alloc((size_t)pairs * splits * 64 * 64);
+    rot.alloc((size_t)pairs * 64 * 64);
+    offmax.alloc(1);
+    sv.alloc(mp);
+    perm.alloc(mp);
+    // round-robin chair rotation: pair k = slots (2k, 2k+1) = (t_k, b_k); t_0 fixed,
+    // t_1 -> t_2 -> ... -> t_{h-1} -> b_{h-1} -> b_{h-2} -> ... -> b_0 -> t_1
+    std::vector<int> pi(nblk);
+    const int h = pairs;
+    for (int s = 0; s < nblk; s++) pi[s] = s;
+    if (h > 1) {
+        pi[0] = 0;
+        for (int k = 1; k < h - 1; k++) pi[2 * k] = 2 * (k + 1);
+        pi[2 * (h - 1)] = 2 * (h - 1) + 1;
+        for (int k = 1; k < h; k++) pi[2 * k + 1] = 2 * (k - 1) + 1;
+        pi[1] = 2;
+    }
+    slotmap.upload(pi);
+    LRN_CUDA(cudaDeviceSynchronize());
+}
+
+int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, double* V, int ldv, double* sigma, SvdWork& w,
+                     double tol, int max_sweeps, cudaStream_t st) {
+    w.ensure(m);
+    const int mp = w.mp, ldw = w.ldw, nblk = mp / 32, pairs = nblk / 2, rounds = nblk - 1;
+    const int rows = m + mp;
+    double* cur = w.buf0.p;
+    double* nxt = w.buf1.p;
+    {
+        dim3 grid((unsigned)cdiv(rows, 256), (unsigned)mp);
+        svd_init_kernel<<<grid, 256, 0, st>>>(A, lda, m, mp, cur, ldw);
+        LRN_CHECK_LAUNCH();
+    }
+    const int splits = w.splits, Kc = w.Kc;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        LRN_CUDA(cudaMemsetAsync(w.offmax.p, 0, sizeof(double), st));
+        for (int r = 0; r < rounds; r++) {
+            GemmParams g;                       // Gram matrices of all column-block pairs (split-K partials)
+            g.A = cur; g.B = cur; g.C = w.gram.p;
+            g.transA = true; g.transB = false;
+            g.M = 64; g.N = 64; g.K = Kc; g.lda = ldw; g.ldb = ldw; g.ldc = 64;
+            g.batch = pairs; g.sA = (long long)64 * ldw; g.sB = (long long)64 * ldw; g.sC = (long long)splits * 4096;
+            g.batch2 = splits; g.sA2 = Kc; g.sB2 = Kc; g.sC2 = 4096;
+            g.K_last = m - (splits - 1) * Kc;
+            gemm(g, st);
+            EigSmallParams e;
+            e.A = w.gram.p; e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; e.n = 64;
+            e.V = w.rot.p; e.ldv = 64; e.sV = 4096; e.relative = 1; e.offmax = w.offmax.p; e.batch = pairs;
+            jacobi_eig_small(e, st);
+            GemmParams u;                       // rotate [A;V] panels and scatter them to next round's arrangement
+            u.A = cur; u.B = w.rot.p; u.C = nxt;
+            u.M = rows; u.N = 64; u.K = 64; u.lda = ldw; u.ldb = 64; u.ldc = ldw;
+            u.batch = pairs; u.sA = (long long)64 * ldw; u.sB = 4096;
+            u.cblkmap = w.slotmap.p;
+            gemm(u, st);
+            std::swap(cur, nxt);
+        }
+        sweeps++;
+        double off = 0.0;
+        LRN_CUDA(cudaMemcpyAsync(&off, w.offmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        if (off <= tol) break;
+    }
+    // after a whole number of sweeps the arrangement is back to the identity; singular values = column norms
+    colnorm_kernel<<<(unsigned)cdiv((long long)mp * 32, 256), 256, 0, st>>>(cur, ldw, m, mp, w.sv.p);
+    LRN_CHECK_LAUNCH();
+    rank_desc_kernel<<<(unsigned)cdiv(mp, 256), 256, 0, st>>>(w.sv.p, mp, w.perm.p);
+    LRN_CHECK_LAUNCH();
+    dim3 grid((unsigned)cdiv(m, 256), (unsigned)m);
+    svd_gather_kernel<<<grid, 256, 0, st>>>(cur, ldw, m, w.perm.p, w.sv.p, U_D, ldu, V, ldv, sigma);
+    LRN_CHECK_LAUNCH();
+    return sweeps;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host tridiagonal QL
+// ---------------------------------------------------------------------------------------------------------------
+bool tridiag_ql(int n, double* d, double* e_in, double* Z, double* zlast) {
+    if (n <= 0) return true;
+    std::vector<double> e(n, 0.0);
+    for (int i = 0; i + 1 < n; i++) e[i] = e_in[i];
+    std::vector<double> zl;
+    if (Z) {
+        for (int i = 0; i < n * n; i++) Z[i] = 0.0;
+        for (int i = 0; i < n; i++) Z[i * n + i] = 1.0;
+    } else if (zlast) {
+        zl.assign(n, 0.0);
+        zl[n - 1] = 1.0;
+    }
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; m++) {
+                double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= eps * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 80) return false;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; i--) {
+                    double f = s * e[i], b = c * e[i];
+                    r = std::hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = c * r - b;
+                    if (Z) {
+                        for (int k = 0; k < n; k++) {
+                            double fz = Z[k * n + i + 1];
+                            Z[k * n + i + 1] = s * Z[k * n + i] + c * fz;
+                            Z[k * n + i] = c * Z[k * n + i] - s * fz;
+                        }
+                    } else if (zlast) {
+                        double fz = zl[i + 1];
+                        zl[i + 1] = s * zl[i] + c * fz;
+                        zl[i] = c * zl[i] - s * fz;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    // ascending sort (selection; n is small)
+    for (int i = 0; i < n - 1; i++) {
+        int k = i;
+        for (int j = i + 1; j < n; j++)
+            if (d[j] < d[k]) k = j;
+        if (k != i) {
+            std::swap(d[i], d[k]);
+            if (Z) for (int r = 0; r < n; r++) std::swap(Z[r * n + i], Z[r * n + k]);
+            else if (zlast) std::swap(zl[i], zl[k]);
+        }
+    }
+    if (zlast) {
+        if (Z) for (int j = 0; j < n; j++) zlast[j] = Z[(n - 1) * n + j];
+        else for (int j = 0; j < n; j++) zlast[j] = zl[j];
+    }
+    return true;
+}
+
+void LanczosWork::ensure(int m_, int kmax_) {
+    if (m_ > m || kmax_ > kmax || !Q.p) {
+        m = std::max(m, m_);
+        kmax = std::max(kmax, kmax_);
+        Q.alloc((size_t)pad_ld(m) * (kmax + 1));
+        w.alloc(pad_ld(m));
+        c.alloc(kmax + 2);
+        S.alloc((size_t)(kmax + 1) * 64);
+    }
+    if (!scal.p) scal.alloc(8);
+    if (!h_scal) LRN_CUDA(cudaMallocHost(&h_scal, 8 * sizeof(double)));
+}
+LanczosWork::~LanczosWork() {
+    if (h_scal) cudaFreeHost(h_scal);
+}
+
+LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_top, double* top_vals_host, double* top_vecs,
+                              int ldv, double tol, LanczosWork& w, cudaStream_t st) {
+    LanczosResult res;
+    LRN_REQUIRE(nev_top >= 0 && nev_top <= 32 && nev_top < m, "nev_top out of range");
+    if (m <= EN) {
+        // direct: all eigenpairs by Jacobi in one CTA
+        w.ensure(EN, EN);
+        EigSmallParams e;
+        e.A = T; e.lda = ld; e.n = m; e.evals = w.c.p; e.sort_desc = 1; e.batch = 1;
+        if (nev_top > 0) { e.V = w.Q.p; e.ldv = pad_ld(w.m); }
+        jacobi_eig_small(e, st);
+        std::vector<double> ev(m);
+        LRN_CUDA(cudaMemcpyAsync(ev.data(), w.c.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        res.lmax = ev[0]; res.lmin = ev[m - 1]; res.iters = 0; res.converged = true;
+        for (int t = 0; t < nev_top; t++) {
+            // ascending tail order: top_vals[0] is the smallest of the nev_top largest
+            int src = nev_top - 1 - t;          // column index in descending order
+            top_vals_host[t] = ev[src];
+            LRN_CUDA(cudaMemcpyAsync(top_vecs + (size_t)t * ldv, w.Q.p + (size_t)src * pad_ld(w.m), m * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, st));
+        }
+        return res;
+    }
+    const int kmax = std::min(m, 500);
+    w.ensure(m, kmax);
+    const int ldq = pad_ld(w.m);
+    double* Q = w.Q.p;
+    std::vector<double> alpha, beta;     // beta[j] couples q_j and q_{j+1}
+    lanczos_init_kernel<<<1, 1024, 0, st>>>(Q, m);
+    LRN_CHECK_LAUNCH();
+    double beta_prev = 0.0;
+    int next_check = 8;
+    std::vector<double> d, e, zl;
+    double scale = 0.0;
+    int k = 0;
+    bool done = false;
+    while (!done) {
+        const int j = k;
+        double* qj = Q + (size_t)j * ldq;
+        gemv_t_kernel<<<(unsigned)cdiv((long long)m * 32, 256), 256, 0, st>>>(T, ld, m, m, qj, w.w.p);
+        LRN_CHECK_LAUNCH();
+        lanczos_alpha_kernel<<<1, 1024, 0, st>>>(w.w.p, qj, j > 0 ? Q + (size_t)(j - 1) * ldq : nullptr, beta_prev, m, w.scal.p);
+        LRN_CHECK_LAUNCH();
+        for (int pass = 0; pass < 2; pass++) {   // full re-orthogonalisation, classical Gram-Schmidt twice
+            gemv_t_kernel<<<(unsigned)cdiv((long long)(j + 1) * 32, 256), 256, 0, st>>>(Q, ldq, m, j + 1, w.w.p, w.c.p);
+            LRN_CHECK_LAUNCH();
+            gemv_n_sub_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(Q, ldq, m, j + 1, w.c.p, w.w.p);
+            LRN_CHECK_LAUNCH();
+        }
+        lanczos_beta_kernel<<<1, 1024, 0, st>>>(w.w.p, Q + (size_t)(j + 1) * ldq, m, w.scal.p);
+        LRN_CHECK_LAUNCH();
+        LRN_CUDA(cudaMemcpyAsync(w.h_scal, w.scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        alpha.push_back(w.h_scal[0]);
+        beta.push_back(w.h_scal[1]);
+        beta_prev = w.h_scal[1];
+        k++;
+        scale = std::max(scale, std::fabs(alpha.back()) + beta_prev);
+        const bool breakdown = !(beta_prev > 1e-13 * scale);
+        if (breakdown || k >= kmax || k >= next_check) {
+            d = alpha;
+            e.assign(beta.begin(), beta.end() - 1);
+            e.push_back(0.0);
+            zl.assign(k, 0.0);
+            tridiag_ql(k, d.data(), e.data(), nullptr, zl.data());
+            double sc = std::max(std::fabs(d[0]), std::fabs(d[k - 1]));
+            if (sc == 0.0) sc = 1.0;
+            bool ok = true;
+            if (want & 1) ok = ok && (std::fabs(beta_prev * zl[0]) <= tol * sc);
+            if (want & 2)
+                for (int t = 0; t < std::max(nev_top, 1) && t < k; t++) ok = ok && (std::fabs(beta_prev * zl[k - 1 - t]) <= tol * sc);
+            res.lmin = d[0];
+            res.lmax = d[k - 1];
+            if (ok || breakdown || k >= kmax) {
+                res.converged = ok || breakdown;
+                done = true;
+            }
+            next_check = k + std::max(4, k / 4);
+        }
+    }
+    res.iters = k;
+    if (nev_top > 0) {
+        std::vector<double> Z((size_t)k * k);
+        d = alpha;
+        e.assign(beta.begin(), beta.end() - 1);
+        e.push_back(0.0);
+        tridiag_ql(k, d.data(), e.data(), Z.data(), nullptr);
+        const int nv = std::min(nev_top, k);
+        std::vector<double> S((size_t)k * nv);
+        for (int t = 0; t < nv; t++) {
+            int src = k - nv + t;              // ascending tail
+            top_vals_host[t] = d[src];
+            for (int i = 0; i < k; i++) S[(size_t)t * k + i] = Z[(size_t)i * k + src];
+        }
+        if ((size_t)k * nv > w.S.n) w.S.alloc((size_t)k * nv);
+        w.S.upload(S.data(), S.size(), st);
+        gemm_nn(st, m, nv, k, 1.0, Q, ldq, w.S.p, k, 0.0, top_vecs, ldv);
+        LRN_CUDA(cudaStreamSynchronize(st));
+    }
+    return res;
+}
+
+}  // namespace lrn

@@ -1,0 +1,83 @@
+// Symmetric eigen / SVD machinery of the NT-scaling and step-length code paths.
+//   * jacobi_eig_small : batched two-sided Jacobi eigensolver for symmetric matrices up to 64x64 (one CTA each, smem).
+//   * svd_block_jacobi : one-sided (Hestenes) block Jacobi SVD of a dense m x m matrix; column-block pairs are
+//                        diagonalised through their 64x64 Gram matrices; all O(m^3) work is DMMA GEMM.
+//                        Replaces FameSVD.fsvd at src/prepare_W.jl:42.
+//   * lanczos_extreme  : extreme eigenpairs of a dense symmetric matrix by Lanczos with full re-orthogonalisation.
+//                        Replaces `eigmin` (src/predictor_corrector.jl:272,285; src/Solvers.jl:503,505) and the
+//                        `eigen(W)` calls of the preconditioners (src/Solvers.jl:642,706), which only use the erank
+//                        largest eigenpairs, the smallest eigenvalue and the trace.
+#pragma once
+#include "common.cuh"
+
+namespace lrn {
+
+struct EigSmallParams {
+    const double* A = nullptr;   // batch of symmetric n x n (full storage), element stride sA; sum of `nparts` partials (stride sPart)
+    int lda = 0;
+    long long sA = 0;
+    int nparts = 1;
+    long long sPart = 0;
+    int n = 0;                   // <= 64
+    double* evals = nullptr;     // optional, n per batch (stride sE); sorted descending if sort_desc
+    long long sE = 0;
+    double* V = nullptr;         // optional eigenvectors (columns), ldv, stride sV
+    int ldv = 0;
+    long long sV = 0;
+    int sort_desc = 0;
+    int relative = 0;            // 1: PD/Gram input, purely relative rotation threshold (high relative accuracy)
+    double* offmax = nullptr;    // optional: atomicMax of max_{i<j} |a_ij|/sqrt(|a_ii a_jj|) of the INPUT matrices
+    double* minval = nullptr;    // optional: per batch smallest eigenvalue (stride 1)
+    int batch = 1;
+};
+void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st);
+
+struct SvdWork {
+    int m = 0, mp = 0;           // mp = m padded to a multiple of 64
+    DevBuf<double> buf0, buf1;   // (m + mp) x mp stacked [A; V] ping-pong buffers, ld = ldw
+    int ldw = 0;
+    DevBuf<double> gram;         // pairs * splits * 64*64
+    DevBuf<double> rot;          // pairs * 64*64
+    DevBuf<double> offmax;       // 1
+    DevBuf<int> slotmap;         // mp/32 : round-robin slot permutation
+    DevBuf<double> sv;           // mp singular values (unsorted)
+    DevBuf<int> perm;            // mp
+    int splits = 1, Kc = 0;
+    void ensure(int m_);
+};
+
+// On return (asynchronous): `U_D` (m x m, ldu) holds A*V = U*diag(sigma) with columns sorted by sigma descending,
+// `V` (m x m, ldv) the right singular vectors in the same order, `sigma` (m) the singular values.
+// Returns the number of sweeps used (host-synchronises once per sweep to read the convergence measure).
+int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, double* V, int ldv, double* sigma, SvdWork& w,
+                     double tol, int max_sweeps, cudaStream_t st);
+
+struct LanczosWork {
+    int m = 0, kmax = 0;
+    DevBuf<double> Q;            // m x (kmax+1)
+    DevBuf<double> w, c;         // m, kmax+1
+    DevBuf<double> scal;         // small device scalars
+    double* h_scal = nullptr;    // pinned host mirror
+    DevBuf<double> S;            // kmax x nev Ritz coefficient upload
+    void ensure(int m_, int kmax_);
+    ~LanczosWork();
+};
+
+struct LanczosResult {
+    double lmin = 0, lmax = 0;
+    int iters = 0;
+    bool converged = false;
+};
+
+// Extreme eigenvalues of the symmetric matrix T (m x m, full storage, ld). If nev_top > 0 also returns the nev_top largest
+// eigenpairs: values in top_vals[0..nev_top) (ascending, like LAPACK's tail) and vectors (m x nev_top, ldv) in top_vecs (device).
+// want: bit0 = smallest eigenvalue must converge, bit1 = largest nev_top must converge.
+LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_top, double* top_vals_host, double* top_vecs,
+                              int ldv, double tol, LanczosWork& w, cudaStream_t st);
+
+// Host-side symmetric tridiagonal eigen-solver (implicit QL). d[k] diag, e[k-1] offdiag. On return d = eigenvalues ascending;
+// if Z != nullptr it must be k x k (row-major identity on input not required) and receives the eigenvectors as columns
+// (Z[i*k + j] = component i of vector j); if zlast != nullptr it receives the last components of every eigenvector.
+bool tridiag_ql(int k, double* d, double* e, double* Z, double* zlast);
+
+}  // namespace lrn

@@ -1,0 +1,253 @@
+// FP64 DMMA GEMM (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the native FP64 tensor shape on sm_100a), cp.async multi-stage
+// shared-memory pipeline with padded, bank-conflict-free operand tiles.
+//
+// Tile shapes:  L = 128x128x16, 8 warps (2x4, warp tile 64x32)   -- large problems, 1 CTA/SM
+//               S =  64x 64x16, 4 warps (2x2, warp tile 32x32)   -- small/medium problems, several CTAs/SM
+// Operand tiles in shared memory are stored along their global-memory contiguous dimension so that every copy is a
+// 16-byte cp.async (8-byte when the caller's pointers/leading dimensions are not 16 B aligned):
+//   "MN-major" tile  [BK][BMN+4]   (operand contiguous along M or N)   fragment read  [k][r] : (k*(BMN+4)+r)  mod 16 distinct
+//   "K-major"  tile  [BMN][BK+4]   (operand contiguous along K)        fragment read  [r][k] : (r*20+k)       mod 16 distinct
+// so each half-warp LDS.64 fragment load touches 16 distinct 8-byte bank pairs (no conflicts).
+#include "gemm.cuh"
+#include <atomic>
+
+namespace lrn {
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int STAGES = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Load one operand tile (BMN x BK of op(X)) into shared memory.
+//   CONTIG_MN = true : global element (r,k) at X[r + k*ld]  -> smem [k][r] with row stride BMN+4
+//   CONTIG_MN = false: global element (r,k) at X[k + r*ld]  -> smem [r][k] with row stride BK+4
+template <int BMN, int NT, bool CONTIG_MN, bool ALIGN16>
+__device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ X, int ld, int r0, int k0,
+                                          int R, int K, int tid) {
+    if (CONTIG_MN) {
+        if (ALIGN16) {
+            constexpr int CH = BMN / 2;              // 16 B chunks per k-line
+            constexpr int TOT = BK * CH;
+#pragma unroll
+            for (int c = tid; c < TOT; c += NT) {
+                int k = c / CH, rc = (c % CH) * 2;
+                int gr = r0 + rc, gk = k0 + k;
+                int bytes = (gk < K) ? min(max((R - gr) * 8, 0), 16) : 0;
+                const double* g = bytes ? (X + (size_t)gk * ld + gr) : X;
+                cp_async16(s + k * (BMN + 4) + rc, g, bytes);
+            }
+        } else {
+            constexpr int TOT = BK * BMN;
+#pragma unroll
+            for (int c = tid; c < TOT; c += NT) {
+                int k = c / BMN, rc = c % BMN;
+                int gr = r0 + rc, gk = k0 + k;
+                int bytes = (gk < K && gr < R) ? 8 : 0;
+                const double* g = bytes ? (X + (size_t)gk * ld + gr) : X;
+                cp_async8(s + k * (BMN + 4) + rc, g, bytes);
+            }
+        }
+    } else {
+        if (ALIGN16) {
+            constexpr int CH = BK / 2;
+            constexpr int TOT = BMN * CH;
+#pragma unroll
+            for (int c = tid; c < TOT; c += NT) {
+                int r = c / CH, kc = (c % CH) * 2;
+                int gr = r0 + r, gk = k0 + kc;
+                int bytes = (gr < R) ? min(max((K - gk) * 8, 0), 16) : 0;
+                const double* g = bytes ? (X + (size_t)gr * ld + gk) : X;
+                cp_async16(s + r * (BK + 4) + kc, g, bytes);
+            }
+        } else {
+            constexpr int TOT = BMN * BK;
+#pragma unroll
+            for (int c = tid; c < TOT; c += NT) {
+                int r = c / BK, kc = c % BK;
+                int gr = r0 + r, gk = k0 + kc;
+                int bytes = (gr < R && gk < K) ? 8 : 0;
+                const double* g = bytes ? (X + (size_t)gr * ld + gk) : X;
+                cp_async8(s + r * (BK + 4) + kc, g, bytes);
+            }
+        }
+    }
+}
+
+template <int BM, int BN>
+struct TileSmem {
+    static constexpr int A_ELEMS = BM * (BK + 4);   // >= BK*(BM+4) for BM >= 16
+    static constexpr int B_ELEMS = BN * (BK + 4);
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, bool ALIGN16>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
+    dgemm_dmma_kernel(const GemmParams p) {
+    constexpr int NT = WARPS_M * WARPS_N * 32;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int MI = WM / 8, NI = WN / 8;
+    using SM = TileSmem<BM, BN>;
+    extern __shared__ __align__(16) double smem[];
+
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (p.lower && (m0 + BM - 1 < n0)) return;
+    const int z = blockIdx.z;
+    const int z1 = z / p.batch2, z2 = z - z1 * p.batch2;
+    const double* __restrict__ A = p.A + (size_t)z1 * p.sA + (size_t)z2 * p.sA2;
+    const double* __restrict__ B = p.B + (size_t)z1 * p.sB + (size_t)z2 * p.sB2;
+    double* __restrict__ C = p.cblkmap ? p.C : p.C + (size_t)z1 * p.sC + (size_t)z2 * p.sC2;
+    const int Kz = (p.K_last > 0 && z2 == p.batch2 - 1) ? p.K_last : p.K;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
+    const int lr = lane >> 2, lk = lane & 3;
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int KT = (Kz + BK - 1) / BK;
+    auto issue = [&](int kt) {
+        double* sA = smem + (size_t)(kt % STAGES) * SM::STAGE_ELEMS;
+        double* sB = sA + SM::A_ELEMS;
+        // op(A) is M x K: !TA -> contiguous along M; TA -> contiguous along K
+        load_tile<BM, NT, !TA, ALIGN16>(sA, A, p.lda, m0, kt * BK, p.M, Kz, tid);
+        // op(B) is K x N: !TB -> contiguous along K; TB -> contiguous along N
+        load_tile<BN, NT, TB, ALIGN16>(sB, B, p.ldb, n0, kt * BK, p.N, Kz, tid);
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < KT) issue(s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
+        cp_async_commit();
+        const double* sA = smem + (size_t)(kt % STAGES) * SM::STAGE_ELEMS;
+        const double* sB = sA + SM::A_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[MI], b[NI];
+#pragma unroll
+            for (int i = 0; i < MI; i++) {
+                int r = wm0 + i * 8 + lr;
+                a[i] = TA ? sA[r * (BK + 4) + kk + lk] : sA[(kk + lk) * (BM + 4) + r];
+            }
+#pragma unroll
+            for (int j = 0; j < NI; j++) {
+                int c = wn0 + j * 8 + lr;
+                b[j] = TB ? sB[(kk + lk) * (BN + 4) + c] : sB[c * (BK + 4) + kk + lk];
+            }
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    const double* cs = p.colscale ? p.colscale + (size_t)z1 * p.sScale : nullptr;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            int col = n0 + wn0 + j * 8 + lk * 2 + t;
+            if (col >= p.N) continue;
+            double sc = cs ? cs[col] : 1.0;
+            int dcol = col;
+            if (p.cblkmap) dcol = p.cblkmap[z1 * (p.N >> 5) + (col >> 5)] * 32 + (col & 31);
+#pragma unroll
+            for (int i = 0; i < MI; i++) {
+                int row = m0 + wm0 + i * 8 + lr;
+                if (row >= p.M) continue;
+                double v = acc[i][j][t] * sc;
+                double* cp = C + (size_t)dcol * p.ldc + row;
+                if (p.mode == 1) v = v * v;
+                v *= alpha;
+                if (beta != 0.0) v += beta * (*cp);
+                *cp = v;
+            }
+        }
+    }
+}
+
+std::atomic<long long> g_launches{0};
+}  // namespace
+std::atomic<long long> g_kernel_launches{0};
+namespace {
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, bool AL>
+void launch_cfg(const GemmParams& p, cudaStream_t st) {
+    auto kern = dgemm_dmma_kernel<BM, BN, WARPS_M, WARPS_N, TA, TB, AL>;
+    static bool configured = false;
+    constexpr size_t smem = TileSmem<BM, BN>::BYTES;
+    if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * p.batch2));
+    kern<<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(p);
+    LRN_CHECK_LAUNCH();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <bool TA, bool TB, bool AL>
+void launch_shape(const GemmParams& p, cudaStream_t st) {
+    long long tilesL = cdiv(p.M, 128) * cdiv(p.N, 128) * (long long)p.batch * p.batch2;
+    if (p.lower) tilesL = tilesL / 2 + cdiv(p.M, 128);
+    if (tilesL >= 100 && p.M > 64 && p.N > 64)
+        launch_cfg<128, 128, 2, 4, TA, TB, AL>(p, st);
+    else
+        launch_cfg<64, 64, 2, 2, TA, TB, AL>(p, st);
+}
+
+template <bool AL>
+void launch_trans(const GemmParams& p, cudaStream_t st) {
+    if (!p.transA && !p.transB) launch_shape<false, false, AL>(p, st);
+    else if (!p.transA && p.transB) launch_shape<false, true, AL>(p, st);
+    else if (p.transA && !p.transB) launch_shape<true, false, AL>(p, st);
+    else launch_shape<true, true, AL>(p, st);
+}
+
+}  // namespace
+
+void gemm(const GemmParams& p, cudaStream_t stream) {
+    if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
+    LRN_REQUIRE(p.A && p.B && p.C, "null operand");
+    LRN_REQUIRE(p.K >= 0, "negative K");
+    bool al = ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && (p.lda % 2 == 0) &&
+              (p.ldb % 2 == 0) && (p.sA % 2 == 0) && (p.sB % 2 == 0) && (p.sA2 % 2 == 0) && (p.sB2 % 2 == 0);
+    LRN_REQUIRE(p.batch2 >= 1, "batch2");
+    LRN_REQUIRE(!p.cblkmap || (p.N % 32 == 0), "cblkmap needs N % 32 == 0");
+    if (al) launch_trans<true>(p, stream);
+    else launch_trans<false>(p, stream);
+}
+
+long long gemm_launch_count() { return g_launches.load(); }
+
+}  // namespace lrn

@@ -1,0 +1,56 @@
+// FP64 tensor-core (DMMA) GEMM family -- the dense workhorse of the library.
+//   C = alpha * op(A) op(B) [.* colscale] + beta * C      (mode 0)
+//   C = beta * C + alpha * (op(A) op(B)).^2               (mode 1, rank-one Schur epilogue, src/makeBBBB.jl:10-14)
+// Column-major, arbitrary sizes, optional batching over blockIdx.z with element strides.
+#pragma once
+#include "common.cuh"
+
+namespace lrn {
+
+struct GemmParams {
+    const double* A = nullptr;
+    const double* B = nullptr;
+    double* C = nullptr;
+    int M = 0, N = 0, K = 0;
+    int lda = 0, ldb = 0, ldc = 0;
+    long long sA = 0, sB = 0, sC = 0;   // batch strides (elements)
+    int batch = 1;
+    bool transA = false, transB = false;
+    double alpha = 1.0, beta = 0.0;
+    int mode = 0;                       // 0 plain, 1 squared-accumulate
+    int lower = 0;                      // 1: skip tiles strictly above the diagonal (symmetric outputs)
+    const double* colscale = nullptr;   // optional length-N scale applied to product columns
+    long long sScale = 0;               // batch stride of colscale
+    // second (inner) batch level: z = z1*batch2 + z2, offsets z1*s? + z2*s?2 (split-K partial products, etc.)
+    int batch2 = 1;
+    long long sA2 = 0, sB2 = 0, sC2 = 0;
+    int K_last = 0;                     // if >0: K used by the last inner index (z2 == batch2-1)
+    // optional scatter of output columns in blocks of 32 (block-Jacobi round-robin re-arrangement):
+    // dest column = cblkmap[z1*(N/32) + col/32]*32 + col%32, C batch strides ignored. N must be a multiple of 32.
+    const int* cblkmap = nullptr;
+};
+
+// Enqueue on `stream`. Never synchronises.
+void gemm(const GemmParams& p, cudaStream_t stream);
+
+// Convenience wrappers (single problem).
+inline void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                    double beta, double* C, int ldc) {
+    GemmParams p; p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.alpha = alpha; p.beta = beta; gemm(p, s);
+}
+inline void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                    double beta, double* C, int ldc) {
+    GemmParams p; p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.alpha = alpha; p.beta = beta; p.transB = true; gemm(p, s);
+}
+inline void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                    double beta, double* C, int ldc) {
+    GemmParams p; p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.alpha = alpha; p.beta = beta; p.transA = true; gemm(p, s);
+}
+
+// Number of DMMA GEMM kernel launches issued so far by this process (bench `gpu_launches` bookkeeping).
+long long gemm_launch_count();
+
+}  // namespace lrn

@@ -1,0 +1,122 @@
+// Elementwise / reduction / sparse kernels of the IP hot path (HBM- or L2-bound work; no tensor cores).
+#pragma once
+#include "common.cuh"
+
+namespace lrn {
+
+// ---- dense m x m elementwise (column-major, separate leading dimensions) -----------------------------------------
+// out = a*A + b*B + c*C   (B, C optional)
+void mat_lincomb(cudaStream_t st, int rows, int cols, double* out, int ldo, double a, const double* A, int lda, double b,
+                 const double* B, int ldb, double c, const double* C, int ldc);
+// out = sym(a*A + b*B + c*C + d*D)  :  out[i,j] = (t[i,j] + t[j,i]) / 2   (square)
+void mat_sym_lincomb(cudaStream_t st, int m, double* out, int ldo, double a, const double* A, int lda, double b,
+                     const double* B, int ldb, double c, const double* C, int ldc, double d, const double* D, int ldd);
+// A <- (A + A^T)/2 in place
+void mat_symmetrize(cudaStream_t st, int m, double* A, int lda);
+// out[i,j] = dd[i] * dd[j] * (T[i,j] + T[j,i]) / 2           (src/predictor_corrector.jl:268-269, :281-282)
+void mat_scaled_sym(cudaStream_t st, int m, double* out, int ldo, const double* T, int ldt, const double* dd);
+// RNT[i,j] = -(T[i,j] + T[j,i]) / (D[i] + D[j])               (src/predictor_corrector.jl:308-309)
+void mat_rnt(cudaStream_t st, int m, double* out, int ldo, const double* T, int ldt, const double* D);
+// T[i,i] += D[i] - sigmamu / D[i];  T -= RNT                  (src/predictor_corrector.jl:186)
+void mat_corr_inner(cudaStream_t st, int m, double* T, int ldt, const double* D, double sigmamu, const double* RNT, int ldr);
+// out[:,j] = in[:,j] * s[j]
+void mat_scale_cols(cudaStream_t st, int rows, int cols, double* out, int ldo, const double* in, int ldi, const double* s);
+// out = in^T
+void mat_transpose(cudaStream_t st, int m, double* out, int ldo, const double* in, int ldi);
+void mat_add_diag(cudaStream_t st, int m, double* A, int lda, double v);
+void mat_set_identity(cudaStream_t st, int m, double* A, int lda, double v);
+// d[j] = sum_i A[i,j] * B[i,j]
+void mat_coldot(cudaStream_t st, int rows, int cols, const double* A, int lda, const double* B, int ldb, double* d);
+// mirror the lower triangle into the upper triangle
+void mat_mirror_lower(cudaStream_t st, int n, double* A, int lda);
+
+// ---- vectors -----------------------------------------------------------------------------------------------------
+enum VecOp {
+    VEC_RECIP = 0,        // out = 1 / a
+    VEC_RSQRT = 1,        // out = 1 / sqrt(a)
+    VEC_POW_M32 = 2,      // out = a^(-3/2)
+    VEC_MUL = 3,          // out = a * b
+    VEC_DIV = 4,          // out = a / b
+    VEC_COPY = 5,
+};
+void vec_op(cudaStream_t st, int n, VecOp op, double* out, const double* a, const double* b);
+// out = alpha*a + beta*b (b optional)
+void vec_axpby(cudaStream_t st, int n, double* out, double alpha, const double* a, double beta, const double* b);
+
+// ---- reductions into a device scalar slot (deterministic two-stage) -------------------------------------------------
+struct Reducer {
+    DevBuf<double> partial;       // per-CTA partials
+    DevBuf<double> slots;         // device result slots
+    double* h_slots = nullptr;    // pinned host mirror
+    int nslots = 0;
+    void init(int nslots_);
+    ~Reducer();
+    // slot += / = result (accumulate flag)
+    void dot_mat(cudaStream_t st, int rows, int cols, const double* A, int lda, const double* B, int ldb, int slot, bool accumulate);
+    void dot_vec(cudaStream_t st, int n, const double* a, const double* b, int slot, bool accumulate) {
+        dot_mat(st, n, 1, a, n, b, n, slot, accumulate);
+    }
+    // slot = min_i a[i]/b[i] (b optional -> min a[i]); combined with previous content when `accumulate`
+    void min_ratio(cudaStream_t st, int n, const double* a, const double* b, int slot, bool accumulate);
+    void zero(cudaStream_t st);
+    // copy all slots to the host mirror and synchronise
+    const double* fetch(cudaStream_t st);
+};
+
+// ---- sparse data of one PSD block --------------------------------------------------------------------------------
+struct SparseBlock {
+    int m = 0, n_var = 0;
+    long long nnz = 0;
+    // by-constraint CSR of AA_i (row j = vec(calA_{i,j}), math sign), entries as (p, q, value)
+    DevBuf<int> rowptr, ep, eq;
+    std::vector<int> h_rowptr, h_part;   // host copies (launch sizing, F1 loop)
+    DevBuf<double> ev;
+    // by-position CSC: distinct (p,q) positions with the list of (constraint, value) that touch them
+    int npos = 0;
+    DevBuf<int> pos_p, pos_q, posptr, pos_row;
+    DevBuf<double> pos_val;
+    // participating constraints (nnz > 0) in nnz-descending (sigmaA) order
+    int npart = 0, nF1 = 0;
+    DevBuf<int> part;
+    int max_row_nnz = 0;
+    bool all_single_diag = false;    // every participating matrix is v * e_a e_a^T
+    // rank-one factors (datarank == -1): CSR n_var x m
+    bool has_B = false;
+    long long nnzB = 0;
+    DevBuf<int> b_rowptr, b_col;
+    DevBuf<double> b_val;
+};
+
+// out[p + q*ld] += scale * sum_{(j,v) at (p,q)} v * y[j]        (mat(AA' y), src/predictor_corrector.jl:13,252; src/Solvers.jl:595)
+void sp_scatter_ATy(cudaStream_t st, const SparseBlock& sb, const double* y, double scale, double* out, int ld);
+// out[j] += scale * sum_e ev * M[ep + eq*ld]                    (AA * vec(M), src/makeBBBB.jl:225 etc.)
+void sp_A_vec(cudaStream_t st, const SparseBlock& sb, const double* M, int ld, double scale, double* out);
+// BG[j + c*ldo] = sum_t B[j,t] G[t,c]                           (B_i * G_i, src/makeBBBB.jl:7)
+void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int ldg, double* BG, int ldo);
+// Sparse-pair Schur term (F3 formula, src/makeBBBB.jl:139-213 / _dot :39-64): for participating positions jj <= kk, both >= first,
+//   H[max(j,k), min(j,k)] += tr(calA_j W calA_k W)
+void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh);
+// F1 column (src/makeBBBB.jl:81-104): given U = W calA_j W dense, H[max(j,k),min(j,k)] += <calA_k, U> for positions kk >= jj
+void sp_schur_f1_column(cudaStream_t st, const SparseBlock& sb, int jj, const double* U, int ldu, double* H, int ldh);
+// densify calA_j into a zeroed m x m buffer
+void sp_densify(cudaStream_t st, const SparseBlock& sb, int j, double* out, int ld);
+
+// ---- LP block (C_lin is n_var x nlin) ----------------------------------------------------------------------------
+struct SparseLin {
+    int n_var = 0, nlin = 0;
+    long long nnz = 0;
+    DevBuf<int> r_ptr, r_col;     // CSR by variable j
+    DevBuf<double> r_val;
+    DevBuf<int> c_ptr, c_row;     // CSC by LP row r
+    DevBuf<double> c_val;
+};
+// out[r] = a*base[r] (base optional) + scale * sum_j C[j,r] y[j]
+void lin_CT_y(cudaStream_t st, const SparseLin& L, const double* y, double scale, double a, const double* base, double* out);
+// out[j] += scale * sum_r C[j,r] x[r]
+void lin_C_x(cudaStream_t st, const SparseLin& L, const double* x, double scale, double* out);
+// H[j,k] += sum_r C[j,r] d[r] C[k,r]   for k <= j              (src/predictor_corrector.jl:36-38)
+void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh);
+// diag[j] += sum_r C[j,r]^2 d[r]
+void lin_schur_diag(cudaStream_t st, const SparseLin& L, const double* d, double* diag);
+
+}  // namespace lrn

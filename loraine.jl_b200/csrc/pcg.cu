@@ -1,0 +1,364 @@
+// kit = 1 path: preconditioned conjugate gradients on the Schur system without forming it.
+//   operator        : MyA functor            src/Solvers.jl:572-614   (solver.cu: apply_A)
+//   preconditioners : MyM_no :616-622, H_beta Prec_for_CG_beta/MyM_beta :624-672,
+//                     H_alpha Prec_for_CG_tilS_prep/prec_alpha_S!/MyM :674-904
+//   recurrence      : ConjugateGradients.jl `cg` (un-vendored; call sites src/predictor_corrector.jl:134,235)
+// The whole recurrence keeps its scalars on the device; the host reads one residual norm per iteration.
+#include "solver.cuh"
+#include <algorithm>
+#include <cmath>
+
+using namespace lrn;
+
+namespace lrn {
+void solver_apply_A(lrn_solver* h, const double* x, double* out);
+}
+
+namespace {
+
+constexpr int TBK = 256;
+inline unsigned nb(long long n) { return (unsigned)cdiv(n, TBK); }
+
+enum { S_GAMMA = 8, S_PAP = 9, S_ALPHA = 10, S_RR = 11, S_ZR = 12, S_BETA = 13, S_FLAG = 14 };
+
+__global__ void k_cg_alpha(double* s) {
+    double a = s[S_GAMMA] / s[S_PAP];
+    s[S_ALPHA] = a;
+    if (isinf(a) || a < 0.0) s[S_FLAG] = 1.0;
+}
+__global__ void k_cg_update(int n, const double* __restrict__ s, const double* __restrict__ p, const double* __restrict__ Ap,
+                            double* __restrict__ x, double* __restrict__ r) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i >= n) return;
+    const double a = s[S_ALPHA];
+    x[i] += a * p[i];
+    r[i] -= a * Ap[i];
+}
+__global__ void k_cg_beta(double* s) { s[S_BETA] = s[S_ZR] / s[S_GAMMA]; }
+__global__ void k_cg_p(int n, const double* __restrict__ s, const double* __restrict__ z, double* __restrict__ p) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i < n) p[i] = z[i] + s[S_BETA] * p[i];
+}
+__global__ void k_fill2(int n, double* a, double v) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+__global__ void k_set_diag(int n, double* A, int lda, const double* d) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i < n) A[(size_t)i * lda + i] = d[i];
+}
+// AU[j,p] = rowscale[j] * sum_q calA_j[p,q] U[q]        (prec_alpha_S!, src/Solvers.jl:833-841)
+__global__ void k_build_AU(int n_var, const int* __restrict__ rowptr, const int* __restrict__ ep, const int* __restrict__ eq,
+                           const double* __restrict__ ev, const double* __restrict__ U, const double* __restrict__ rowscale,
+                           double* __restrict__ AU, int ld) {
+    int j = blockIdx.x * TBK + threadIdx.x;
+    if (j >= n_var) return;
+    const double sc = rowscale ? rowscale[j] : 1.0;
+    for (int e = rowptr[j]; e < rowptr[j + 1]; e++) AU[(size_t)ep[e] * ld + j] += sc * ev[e] * U[eq[e]];
+}
+// out[j] += sum_e v_e * sum_r ZY[p_e, r] * U[q_e, r]     (AA * kron(U, Z y), src/Solvers.jl:891-896)
+__global__ void k_A_vec_rank(int n_var, const int* __restrict__ rowptr, const int* __restrict__ ep, const int* __restrict__ eq,
+                             const double* __restrict__ ev, const double* __restrict__ ZY, int ldz,
+                             const double* __restrict__ U, int ldu, int k, double* __restrict__ out) {
+    int j = blockIdx.x * TBK + threadIdx.x;
+    if (j >= n_var) return;
+    int e0 = rowptr[j], e1 = rowptr[j + 1];
+    if (e0 == e1) return;
+    double s = 0.0;
+    for (int e = e0; e < e1; e++) {
+        double t = 0.0;
+        for (int r = 0; r < k; r++) t += ZY[(size_t)r * ldz + ep[e]] * U[(size_t)r * ldu + eq[e]];
+        s += ev[e] * t;
+    }
+    out[j] += s;
+}
+
+struct PhaseT {   // minimal event timer (same bookkeeping as solver.cu)
+    lrn_solver* h; PhaseEvt e;
+    PhaseT(lrn_solver* h_, int phase) : h(h_) {
+        e.phase = phase;
+        auto take = [&]() {
+            if (h->evpool.empty()) { cudaEvent_t ev; LRN_CUDA(cudaEventCreate(&ev)); return ev; }
+            cudaEvent_t ev = h->evpool.back(); h->evpool.pop_back(); return ev;
+        };
+        e.a = take(); e.b = take();
+        LRN_CUDA(cudaEventRecord(e.a, h->st));
+    }
+    ~PhaseT() { cudaEventRecord(e.b, h->st); h->pending.push_back(e); h->t_calls[e.phase]++; }
+};
+
+template <typename F>
+int32_t guarded(lrn_solver* h, F&& f) {
+    if (!h) return LRN_ERR_ARG;
+    try {
+        LRN_CUDA(cudaSetDevice(h->device));
+        return f();
+    } catch (const std::invalid_argument& e) { h->err = e.what(); return LRN_ERR_ARG;
+    } catch (const CudaError& e) { h->err = e.what(); return LRN_ERR_CUDA;
+    } catch (const std::exception& e) { h->err = e.what(); return LRN_ERR_STATE; }
+}
+
+// out = D^{-1} x   (AAAATtau \ x, src/Solvers.jl:874,900)
+void d_solve(lrn_solver* h, const double* x, double* out) {
+    cudaStream_t st = h->st;
+    if (h->pDense) {
+        LRN_CUDA(cudaMemcpyAsync(out, x, h->n_var * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        chol_solve(h->pDd.p(), h->n_var, h->pDd.ld, h->cholD, out, h->tn1.p, 3, st);
+    } else {
+        vec_op(st, h->n_var, VEC_DIV, out, x, h->pDiag.p);
+    }
+}
+
+// tau of one block from the extreme eigenvalues of W (src/Solvers.jl:642-650, :706-719)
+int block_tau(lrn_solver* h, Block& B, int k, std::vector<double>& top_vals) {
+    cudaStream_t st = h->st;
+    const int m = B.m, ld = B.ld;
+    if (!B.U.p()) { B.U.init(m, k); B.MU.init(m, k); B.ZY.init(m, k); B.Zf.init(m, m); }
+    top_vals.assign(k, 0.0);
+    const double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-10;
+    LanczosResult r = lanczos_extreme(B.W.p(), m, ld, 3, k, top_vals.data(), B.U.p(), B.U.ld, tol, h->lan, st);
+    h->stat_lanczos_iters += r.iters;
+    if (!r.converged) h->stat_lanczos_fail++;
+    h->red.dot_mat(st, 1, m, B.W.p(), ld + 1, h->ones.p, 1, 15, false);    // trace(W)
+    const double* s = h->red.fetch(st);
+    const double tr = s[15];
+    double sum_l = 0.0;
+    for (double v : top_vals) sum_l += v;
+    const double min_s = r.lmin, mean_s = (tr - sum_l) / (double)(m - k);
+    B.tau = (h->opt.aamat == 0) ? min_s : (min_s + mean_s) / 2.0 - 1.0e-14;
+    return 0;
+}
+
+void prec_beta(lrn_solver* h) {
+    cudaStream_t st = h->st;
+    const int n = h->n_var, k = h->opt.erank;
+    if (!h->pDiag.p) { h->pDiag.alloc(n); h->pDsq.alloc(n); }
+    double shift = 0.0;
+    std::vector<double> tv;
+    for (auto& B : h->blk) {
+        block_tau(h, B, k, tv);
+        if (h->opt.aamat < 3) shift += B.tau * B.tau;
+    }
+    k_fill2<<<nb(n), TBK, 0, st>>>(n, h->pDiag.p, shift);
+    if (h->nlmi > 0 && h->nlin > 0) {
+        vec_op(st, h->nlin, VEC_MUL, h->tl1.p, h->x_lin.p, h->si_lin.p);
+        lin_schur_diag(st, h->lin, h->tl1.p, h->pDiag.p);
+    }
+    h->pDense = false;
+}
+
+int32_t prec_alpha(lrn_solver* h) {
+    cudaStream_t st = h->st;
+    const int n = h->n_var, k = h->opt.erank;
+    LRN_REQUIRE(k >= 1, "erank must be >= 1 for the H_alpha preconditioner");
+    if (!h->pDiag.p) { h->pDiag.alloc(n); h->pDsq.alloc(n); }
+    int kS = 0, maxm = 1;
+    for (auto& B : h->blk) { kS += k * B.m; maxm = std::max(maxm, B.m); }
+    const int ldt = pad_ld(n);
+    if (h->kS != kS || !h->pT.p) {
+        h->kS = kS;
+        h->pT.alloc((size_t)ldt * kS);
+        h->pS.alloc((size_t)pad_ld(kS) * kS);
+        h->pY.alloc(kS);
+        h->pAU.alloc((size_t)ldt * maxm);
+    }
+    double shift = 0.0;
+    std::vector<double> tv, sc(k);
+    for (auto& B : h->blk) {
+        const int m = B.m, ld = B.ld;
+        block_tau(h, B, k, tv);
+        if (h->opt.aamat < 3) shift += B.tau * B.tau;
+        // Umat = vect_l * sqrt(lambda_l - tau)                                   (src/Solvers.jl:721-722)
+        for (int r = 0; r < k; r++) sc[r] = std::sqrt(std::max(tv[r] - B.tau, 0.0));
+        LRN_CUDA(cudaMemcpyAsync(B.vtmp.p, sc.data(), k * sizeof(double), cudaMemcpyHostToDevice, st));
+        mat_scale_cols(st, m, k, B.U.p(), B.U.ld, B.U.p(), B.U.ld, B.vtmp.p);
+        // Z = chol(2 W0 + U U').L with W0 = W - U U'                             (src/Solvers.jl:725-731)
+        mat_lincomb(st, m, m, B.Zf.p(), ld, 2.0, B.W.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
+        gemm_nt(st, m, m, k, -1.0, B.U.p(), B.U.ld, B.U.p(), B.U.ld, 1.0, B.Zf.p(), ld);
+        cholesky_lower(B.Zf.p(), m, ld, B.cholX, st);     // cholX workspace is free between prepare_W calls
+        int info = 0;
+        LRN_CUDA(cudaMemcpyAsync(&info, B.cholX.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        B.chol_cached = false;
+        if (info != 0) return info;
+        zero_strict_upper(B.Zf.p(), m, ld, st);
+    }
+    // AAAATtau = sum tau_i^2 I (+ C_lin diag(x./s) C_lin')                        (src/Solvers.jl:734-745)
+    k_fill2<<<nb(n), TBK, 0, st>>>(n, h->pDiag.p, shift);
+    h->pDense = false;
+    if (h->nlin > 0) {
+        vec_op(st, h->nlin, VEC_MUL, h->tl1.p, h->x_lin.p, h->si_lin.p);
+        if (!h->pDd.p()) h->pDd.init(n, n);
+        LRN_CUDA(cudaMemsetAsync(h->pDd.p(), 0, h->pDd.bytes(), st));
+        lin_schur(st, h->lin, h->tl1.p, h->pDd.p(), h->pDd.ld);
+        lin_schur_diag(st, h->lin, h->tl1.p, h->pDiag.p);
+        k_set_diag<<<nb(n), TBK, 0, st>>>(n, h->pDd.p(), h->pDd.ld, h->pDiag.p);
+        cholesky_lower(h->pDd.p(), n, h->pDd.ld, h->cholD, st);
+        int info = 0;
+        LRN_CUDA(cudaMemcpyAsync(&info, h->cholD.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        if (info != 0) return info;
+        h->pDense = true;
+    }
+    vec_op(st, n, VEC_RSQRT, h->pDsq.p, h->pDiag.p, nullptr);
+    // t = [AA_i kron(U_i, Z_i)]_i ; fast formula scales rows by diag(AAAATtau)^{-1/2}   (src/Solvers.jl:752-801, :819-864)
+    const bool fast = (!h->pDense) || k == 1;
+    int off = 0;
+    for (auto& B : h->blk) {
+        const int m = B.m;
+        for (int r = 0; r < k; r++) {
+            LRN_CUDA(cudaMemsetAsync(h->pAU.p, 0, (size_t)ldt * m * sizeof(double), st));
+            k_build_AU<<<nb(n), TBK, 0, st>>>(n, B.sp.rowptr.p, B.sp.ep.p, B.sp.eq.p, B.sp.ev.p, B.U.p() + (size_t)r * B.U.ld,
+                                              fast ? h->pDsq.p : nullptr, h->pAU.p, ldt);
+            gemm_nn(st, n, m, m, 1.0, h->pAU.p, ldt, B.Zf.p(), B.ld, 0.0, h->pT.p + (size_t)(off + r * m) * ldt, ldt);
+        }
+        off += k * m;
+    }
+    const int lds = pad_ld(kS);
+    if (fast) {
+        gemm_tn(st, kS, kS, n, 1.0, h->pT.p, ldt, h->pT.p, ldt, 0.0, h->pS.p, lds);
+    } else {
+        // S = t' * (AAAATtau \ t), column by column (only for erank > 1 together with an LP block)
+        DevBuf<double> DT((size_t)ldt * kS);
+        for (int c = 0; c < kS; c++) d_solve(h, h->pT.p + (size_t)c * ldt, DT.p + (size_t)c * ldt);
+        gemm_tn(st, kS, kS, n, 1.0, h->pT.p, ldt, DT.p, ldt, 0.0, h->pS.p, lds);
+        LRN_CUDA(cudaStreamSynchronize(st));
+    }
+    // S = (S + S')/2 + I ; cholS = cholesky(S)                                    (src/Solvers.jl:804-805)
+    mat_symmetrize(st, kS, h->pS.p, lds);
+    mat_add_diag(st, kS, h->pS.p, lds, 1.0);
+    cholesky_lower(h->pS.p, kS, lds, h->cholS, st);
+    int info = 0;
+    LRN_CUDA(cudaMemcpyAsync(&info, h->cholS.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    LRN_CUDA(cudaStreamSynchronize(st));
+    return info;
+}
+
+// Mx = M^{-1} x for the H_alpha preconditioner (MyM functor, src/Solvers.jl:866-904)
+void apply_alpha(lrn_solver* h, const double* x, double* out) {
+    cudaStream_t st = h->st;
+    const int n = h->n_var, k = h->opt.erank;
+    double* v = h->tn2.p;
+    d_solve(h, x, v);
+    int off = 0;
+    for (auto& B : h->blk) {
+        const int m = B.m, ld = B.ld;
+        LRN_CUDA(cudaMemsetAsync(B.T1.p(), 0, B.T1.bytes(), st));
+        sp_scatter_ATy(st, B.sp, v, 1.0, B.T1.p(), ld);
+        gemm_nn(st, m, k, m, 1.0, B.T1.p(), ld, B.U.p(), B.U.ld, 0.0, B.MU.p(), B.MU.ld);
+        gemm_tn(st, m, k, m, 1.0, B.Zf.p(), ld, B.MU.p(), B.MU.ld, 0.0, h->pY.p + off, m);
+        off += k * m;
+    }
+    chol_solve(h->pS.p, h->kS, pad_ld(h->kS), h->cholS, h->pY.p, h->pT.p /* scratch: t is only needed while S is being built */,
+               3, st);
+    double* yy2 = h->cg_Ap.p;     // free while the preconditioner runs
+    LRN_CUDA(cudaMemsetAsync(yy2, 0, n * sizeof(double), st));
+    off = 0;
+    for (auto& B : h->blk) {
+        const int m = B.m, ld = B.ld;
+        gemm_nn(st, m, k, m, 1.0, B.Zf.p(), ld, h->pY.p + off, m, 0.0, B.ZY.p(), B.ZY.ld);
+        k_A_vec_rank<<<nb(n), TBK, 0, st>>>(n, B.sp.rowptr.p, B.sp.ep.p, B.sp.eq.p, B.sp.ev.p, B.ZY.p(), B.ZY.ld, B.U.p(),
+                                            B.U.ld, k, yy2);
+        off += k * m;
+    }
+    d_solve(h, yy2, out);
+    vec_axpby(st, n, out, 1.0, v, -1.0, out);
+}
+
+void apply_prec(lrn_solver* h, int kind, const double* r, double* z) {
+    cudaStream_t st = h->st;
+    if (kind == 0) LRN_CUDA(cudaMemcpyAsync(z, r, h->n_var * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else if (kind == 1) apply_alpha(h, r, z);
+    else vec_op(st, h->n_var, VEC_DIV, z, r, h->pDiag.p);
+}
+
+void ensure_cg(lrn_solver* h) {
+    if (!h->cg_r.p) {
+        for (auto* v : {&h->cg_r, &h->cg_z, &h->cg_p, &h->cg_Ap}) v->alloc(h->n_var);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lrn_prec_prepare(lrn_handle_t h, int32_t kind) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(h->finalized && h->nlmi > 0, "preconditioners need at least one PSD block");
+        PhaseT ph(h, LRN_T_PREC);
+        ensure_cg(h);
+        int32_t rc = LRN_OK;
+        if (kind == 1) rc = prec_alpha(h);
+        else if (kind == 2 || kind == 4) prec_beta(h);
+        else if (kind != 0) { h->err = "preconditioner kind must be 0, 1, 2 or 4"; return LRN_ERR_ARG; }
+        h->prec_ready = kind;
+        return rc;
+    });
+}
+
+int32_t lrn_pcg(lrn_handle_t h, double tol, int64_t max_iter, int32_t kind, int64_t* num_iters, int32_t* exit_code) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(num_iters && exit_code, "null outputs");
+        LRN_REQUIRE(kind == 0 || kind == 1 || kind == 2 || kind == 4, "bad preconditioner kind");
+        LRN_REQUIRE(kind == 0 || h->prec_ready == kind || (kind != 1 && (h->prec_ready == 2 || h->prec_ready == 4)),
+                    "preconditioner not prepared (lrn_prec_prepare)");
+        PhaseT ph(h, LRN_T_CG);
+        ensure_cg(h);
+        cudaStream_t st = h->st;
+        const int n = h->n_var;
+        Reducer& R = h->red;
+        double* x = h->dely.p;
+        double *r = h->cg_r.p, *z = h->cg_z.p, *p = h->cg_p.p, *Ap = h->cg_Ap.p;
+        const double* b = h->rhs.p;
+        LRN_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st));
+        R.zero(st);
+        R.dot_vec(st, n, b, b, S_RR, false);
+        const double* s = R.fetch(st);
+        *num_iters = 0;
+        if (std::sqrt(s[S_RR]) == 0.0) { *exit_code = 1; return LRN_OK; }
+        // r = b - A*0 = b
+        LRN_CUDA(cudaMemcpyAsync(r, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        const double res0 = std::sqrt(s[S_RR]);
+        if (res0 <= tol) { *exit_code = 2; return LRN_OK; }
+        apply_prec(h, kind, r, z);
+        LRN_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (int64_t it = 1; it <= max_iter; it++) {
+            solver_apply_A(h, p, Ap);
+            R.dot_vec(st, n, r, z, S_GAMMA, false);
+            R.dot_vec(st, n, p, Ap, S_PAP, false);
+            k_cg_alpha<<<1, 1, 0, st>>>(R.slots.p);
+            k_cg_update<<<nb(n), TBK, 0, st>>>(n, R.slots.p, p, Ap, x, r);
+            R.dot_vec(st, n, r, r, S_RR, false);
+            LRN_CHECK_LAUNCH();
+            s = R.fetch(st);
+            if (s[S_FLAG] != 0.0 || std::isnan(s[S_ALPHA])) { *exit_code = -13; *num_iters = it; return LRN_OK; }
+            if (std::sqrt(s[S_RR]) / res0 <= tol) { *exit_code = 30; *num_iters = it; return LRN_OK; }
+            apply_prec(h, kind, r, z);
+            R.dot_vec(st, n, z, r, S_ZR, false);
+            k_cg_beta<<<1, 1, 0, st>>>(R.slots.p);
+            k_cg_p<<<nb(n), TBK, 0, st>>>(n, R.slots.p, z, p);
+            LRN_CHECK_LAUNCH();
+        }
+        *exit_code = -2;
+        *num_iters = max_iter;
+        LRN_CUDA(cudaStreamSynchronize(st));
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_apply_operator(lrn_handle_t h, int32_t kind, const double* x, double* out) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(x && out, "null pointers");
+        ensure_cg(h);
+        cudaStream_t st = h->st;
+        const int n = h->n_var;
+        h->cg_p.upload(x, n, st);
+        if (kind == -1) solver_apply_A(h, h->cg_p.p, h->cg_z.p);
+        else apply_prec(h, kind, h->cg_p.p, h->cg_z.p);
+        LRN_CUDA(cudaMemcpyAsync(out, h->cg_z.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        return LRN_OK;
+    });
+}
+
+}  // extern "C"

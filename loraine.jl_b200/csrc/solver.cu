@@ -1,0 +1,1000 @@
+// C ABI + device-resident interior-point state.  Every entry point cites the reference lines it replaces in
+// include/loraine_b200.h.  No CPU fallback: all arithmetic of the hot path runs in the kernels of gemm.cu / chol.cu /
+// eig.cu / ops.cu and in the small kernels below.
+#include "solver.cuh"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+using namespace lrn;
+
+namespace {
+
+constexpr int TBK = 256;
+
+// ---- small LP-block kernels (vectors of length nlin) -------------------------------------------------------------------
+// predictor: t = (x .* si) .* rd + x                                             (src/predictor_corrector.jl:49)
+// corrector: t = (x .* si) .* rd + x + (dx .* ds) .* si - sigmamu .* si          (src/predictor_corrector.jl:190-191)
+__global__ void k_lp_rhs(int n, int corr, double sigmamu, const double* x, const double* si, const double* rd,
+                         const double* dx, const double* ds, double* t) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i >= n) return;
+    double v = (x[i] * si[i]) * rd[i] + x[i];
+    if (corr) v += (dx[i] * ds[i]) * si[i] - sigmamu * si[i];
+    t[i] = v;
+}
+// find_step_lin, src/predictor_corrector.jl:330-335:  dx = -x - x.*si.*ds [+ sigmamu.*si + rnt]
+__global__ void k_lp_dx(int n, int corr, double sigmamu, const double* x, const double* si, const double* ds,
+                        const double* rnt, double* dx) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i >= n) return;
+    double v = -x[i] - x[i] * si[i] * ds[i];
+    if (corr) v += sigmamu * si[i] + rnt[i];
+    dx[i] = v;
+}
+// src/predictor_corrector.jl:351-354
+__global__ void k_lp_pred_update(int n, double a, double b, const double* x, const double* s, const double* dx,
+                                 const double* ds, const double* si, double* xn, double* sn, double* rnt) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i >= n) return;
+    xn[i] = x[i] + a * dx[i];
+    sn[i] = s[i] + b * ds[i];
+    rnt[i] = -(dx[i] * ds[i]) * si[i];
+}
+// CG operator LP part: t = (x .* sinv) .* t                                       (src/Solvers.jl:609)
+__global__ void k_mul3(int n, const double* a, const double* b, double* t) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i < n) t[i] = (a[i] * b[i]) * t[i];
+}
+__global__ void k_fill(int n, double* a, double v) {
+    int i = blockIdx.x * TBK + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+inline unsigned nb(long long n) { return (unsigned)cdiv(n, TBK); }
+
+// ---- error / timer plumbing ------------------------------------------------------------------------------------------
+struct Phase {
+    lrn_solver* h;
+    PhaseEvt e;
+    Phase(lrn_solver* h_, int phase) : h(h_) {
+        e.phase = phase;
+        auto take = [&]() {
+            if (h->evpool.empty()) {
+                cudaEvent_t ev;
+                LRN_CUDA(cudaEventCreate(&ev));
+                return ev;
+            }
+            cudaEvent_t ev = h->evpool.back();
+            h->evpool.pop_back();
+            return ev;
+        };
+        e.a = take();
+        e.b = take();
+        LRN_CUDA(cudaEventRecord(e.a, h->st));
+    }
+    ~Phase() {
+        cudaEventRecord(e.b, h->st);
+        h->pending.push_back(e);
+        h->t_calls[e.phase]++;
+    }
+};
+
+void flush_timers(lrn_solver* h) {
+    if (h->pending.empty()) return;
+    LRN_CUDA(cudaStreamSynchronize(h->st));
+    for (auto& e : h->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) h->t_ms[e.phase] += ms;
+        h->evpool.push_back(e.a);
+        h->evpool.push_back(e.b);
+    }
+    h->pending.clear();
+}
+
+template <typename F>
+int32_t guarded(lrn_solver* h, F&& f) {
+    if (!h) return LRN_ERR_ARG;
+    try {
+        LRN_CUDA(cudaSetDevice(h->device));
+        int32_t r = f();
+        if (h->pending.size() > 512) flush_timers(h);
+        return r;
+    } catch (const std::invalid_argument& e) {
+        h->err = e.what();
+        return LRN_ERR_ARG;
+    } catch (const CudaError& e) {
+        h->err = e.what();
+        return LRN_ERR_CUDA;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return LRN_ERR_STATE;
+    }
+}
+
+void upload_dense(lrn_solver* h, DMat& M, const double* host) {
+    LRN_CUDA(cudaMemcpy2DAsync(M.p(), (size_t)M.ld * sizeof(double), host, (size_t)M.rows * sizeof(double),
+                               (size_t)M.rows * sizeof(double), M.cols, cudaMemcpyHostToDevice, h->st));
+}
+void download_dense(lrn_solver* h, const double* dev, int ld, int rows, int cols, double* host) {
+    LRN_CUDA(cudaMemcpy2DAsync(host, (size_t)rows * sizeof(double), dev, (size_t)ld * sizeof(double),
+                               (size_t)rows * sizeof(double), cols, cudaMemcpyDeviceToHost, h->st));
+}
+
+void copy_csc(HostCSC& dst, int64_t ncol, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    LRN_REQUIRE(colptr && colptr[0] == 1, "colptr must be 1-based (Julia SparseMatrixCSC)");
+    dst.colptr.assign(colptr, colptr + ncol + 1);
+    const int64_t nnz = colptr[ncol] - 1;
+    LRN_REQUIRE(nnz >= 0 && nnz < 2000000000LL, "nnz out of range");
+    LRN_REQUIRE(nnz == 0 || (rowval && nzval), "null rowval/nzval");
+    dst.rowval.assign(rowval, rowval + nnz);
+    dst.nzval.assign(nzval, nzval + nnz);
+    for (auto& c : dst.colptr) c -= 1;
+    for (auto& r : dst.rowval) r -= 1;
+    dst.set = true;
+}
+
+// Build the device structures of one PSD block from the staged Julia CSC of AA_i (n_var x m^2).
+void build_block(lrn_solver* h, Block& B) {
+    const int m = B.m, n = h->n_var;
+    SparseBlock& sp = B.sp;
+    sp.m = m;
+    sp.n_var = n;
+    LRN_REQUIRE(B.hAA.set, "lrn_set_block_AA was not called for every block");
+    const auto& cp = B.hAA.colptr;
+    const auto& rv = B.hAA.rowval;
+    const auto& nz = B.hAA.nzval;
+    const int64_t nnz = (int64_t)rv.size();
+    sp.nnz = nnz;
+    std::vector<int> rowptr(n + 1, 0);
+    for (int64_t e = 0; e < nnz; e++) {
+        LRN_REQUIRE(rv[e] >= 0 && rv[e] < n, "AA row index out of range");
+        rowptr[rv[e] + 1]++;
+    }
+    for (int j = 0; j < n; j++) rowptr[j + 1] += rowptr[j];
+    std::vector<int> ep(nnz), eq(nnz), fill(rowptr.begin(), rowptr.end() - 1);
+    std::vector<double> ev(nnz);
+    std::vector<int> pos_p, pos_q, posptr, pos_row((size_t)nnz);
+    std::vector<double> pos_val((size_t)nnz);
+    posptr.push_back(0);
+    const int64_t ncol = (int64_t)m * m;
+    int64_t w = 0;
+    for (int64_t c = 0; c < ncol; c++) {
+        if (cp[c + 1] == cp[c]) continue;
+        const int p = (int)(c % m), q = (int)(c / m);
+        for (int64_t e = cp[c]; e < cp[c + 1]; e++) {
+            const int j = (int)rv[e];
+            const int dst = fill[j]++;
+            ep[dst] = p; eq[dst] = q; ev[dst] = nz[e];
+            pos_row[w] = j; pos_val[w] = nz[e];
+            w++;
+        }
+        pos_p.push_back(p); pos_q.push_back(q); posptr.push_back((int)w);
+    }
+    sp.npos = (int)pos_p.size();
+    // participating constraints in nnz-descending stable order (= sigmaA restricted to nnz > 0, src/model.jl:157-160)
+    std::vector<int> part;
+    for (int j = 0; j < n; j++) if (rowptr[j + 1] > rowptr[j]) part.push_back(j);
+    std::stable_sort(part.begin(), part.end(), [&](int a, int b2) {
+        return (rowptr[a + 1] - rowptr[a]) > (rowptr[b2 + 1] - rowptr[b2]);
+    });
+    sp.npart = (int)part.size();
+    sp.max_row_nnz = sp.npart ? rowptr[part[0] + 1] - rowptr[part[0]] : 0;
+    // F1 / F3 split: a prefix of the nnz-sorted list uses the dense formula
+    int nF1 = 0;
+    if (h->opt.schur_split == 1) {
+        for (int jj = 0; jj < sp.npart; jj++) {
+            int nzj = rowptr[part[jj] + 1] - rowptr[part[jj]];
+            if (nzj > h->opt.datasparsity) nF1 = jj + 1; else break;
+        }
+    } else {
+        // cost model: F3_j ~ nnz_j * sum_{k>=j} nnz_k gathered pairs, F1_j ~ 4 m^3 tensor flops + launches
+        double suffix = 0.0;
+        std::vector<double> suf(sp.npart + 1, 0.0);
+        for (int jj = sp.npart - 1; jj >= 0; jj--) {
+            suffix += rowptr[part[jj] + 1] - rowptr[part[jj]];
+            suf[jj] = suffix;
+        }
+        for (int jj = 0; jj < sp.npart; jj++) {
+            double nzj = rowptr[part[jj] + 1] - rowptr[part[jj]];
+            if (nzj * suf[jj] > 0.13 * (double)m * m * m + 2.0e7) nF1 = jj + 1; else break;
+        }
+    }
+    sp.nF1 = nF1;
+    sp.h_rowptr = rowptr;
+    sp.h_part = part;
+    sp.rowptr.upload(rowptr, h->st); sp.ep.upload(ep, h->st); sp.eq.upload(eq, h->st); sp.ev.upload(ev, h->st);
+    sp.pos_p.upload(pos_p, h->st); sp.pos_q.upload(pos_q, h->st); sp.posptr.upload(posptr, h->st);
+    sp.pos_row.upload(pos_row, h->st); sp.pos_val.upload(pos_val, h->st);
+    sp.part.upload(part, h->st);
+    // rank-one factors: Julia CSC n_var x m  ->  CSR by constraint
+    if (B.hB.set) {
+        const auto& bc = B.hB.colptr;
+        const int64_t bn = (int64_t)B.hB.rowval.size();
+        std::vector<int> brp(n + 1, 0), bcol(bn);
+        std::vector<double> bval(bn);
+        for (int64_t e = 0; e < bn; e++) brp[B.hB.rowval[e] + 1]++;
+        for (int j = 0; j < n; j++) brp[j + 1] += brp[j];
+        std::vector<int> f2(brp.begin(), brp.end() - 1);
+        for (int c = 0; c < m; c++)
+            for (int64_t e = bc[c]; e < bc[c + 1]; e++) {
+                int dst = f2[B.hB.rowval[e]]++;
+                bcol[dst] = c; bval[dst] = B.hB.nzval[e];
+            }
+        sp.has_B = bn > 0;
+        sp.nnzB = bn;
+        sp.b_rowptr.upload(brp, h->st); sp.b_col.upload(bcol, h->st); sp.b_val.upload(bval, h->st);
+    }
+    // dense C_i
+    B.C.init(m, m);
+    double nc = 0.0;
+    if (B.hC.set) {
+        std::vector<double> Cd((size_t)B.C.ld * m, 0.0);
+        for (int c = 0; c < m; c++)
+            for (int64_t e = B.hC.colptr[c]; e < B.hC.colptr[c + 1]; e++) {
+                Cd[(size_t)c * B.C.ld + B.hC.rowval[e]] += B.hC.nzval[e];
+            }
+        for (int c = 0; c < m; c++)
+            for (int r = 0; r < m; r++) nc += Cd[(size_t)c * B.C.ld + r] * Cd[(size_t)c * B.C.ld + r];
+        B.C.buf.upload(Cd.data(), Cd.size(), h->st);
+    }
+    B.normC = std::sqrt(nc);
+    LRN_CUDA(cudaStreamSynchronize(h->st));
+    B.hAA = HostCSC(); B.hB = HostCSC(); B.hC = HostCSC();
+    for (DMat* M : {&B.X, &B.S, &B.dX, &B.dS, &B.Xn, &B.Sn, &B.G, &B.Gi, &B.W, &B.Si, &B.Rd, &B.RNT, &B.LX, &B.LS, &B.T1, &B.T2, &B.T3})
+        M->init(m, m);
+    B.ld = B.X.ld;
+    B.D.alloc(m); B.DDsi.alloc(m); B.dm12.alloc(m); B.dm32.alloc(m); B.vtmp.alloc(m);
+}
+
+// smallest eigenvalue of the symmetric m x m matrix T (device)
+double lambda_min(lrn_solver* h, const double* T, int m, int ld) {
+    Phase ph(h, LRN_T_EIGMIN);
+    double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-10;
+    LanczosResult r = lanczos_extreme(T, m, ld, 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st);
+    h->stat_lanczos_iters += r.iters;
+    if (!r.converged) h->stat_lanczos_fail++;
+    return r.lmin;
+}
+
+inline double steplen(double mimi, double tau) { return (mimi > -1e-6) ? 0.99 : std::min(1.0, -tau / mimi); }
+
+// Factor X (or S) of block `B` into L with the reference's try_cholesky retry loop (src/prepare_W.jl:5-26).
+bool try_cholesky(lrn_solver* h, DMat& X, DMat& L, CholWork& cw) {
+    const int m = X.rows;
+    for (int icount = 0;; icount++) {
+        LRN_CUDA(cudaMemcpyAsync(L.p(), X.p(), X.bytes(), cudaMemcpyDeviceToDevice, h->st));
+        cholesky_lower(L.p(), m, L.ld, cw, h->st);
+        int info = 0;
+        LRN_CUDA(cudaMemcpyAsync(&info, cw.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        if (info == 0) return true;
+        if (icount >= 1000) {
+            mat_set_identity(h->st, m, L.p(), L.ld, 1.0);
+            cholesky_lower(L.p(), m, L.ld, cw, h->st);   // keeps dinv consistent with the identity factor
+            return false;
+        }
+        mat_add_diag(h->st, m, X.p(), X.ld, 1e-5);
+    }
+}
+
+// out = A x  (MyA functor, src/Solvers.jl:582-614)
+void apply_A(lrn_solver* h, const double* x, double* out) {
+    cudaStream_t st = h->st;
+    LRN_CUDA(cudaMemsetAsync(out, 0, (size_t)h->n_var * sizeof(double), st));
+    for (auto& B : h->blk) {
+        const int m = B.m, ld = B.ld;
+        LRN_CUDA(cudaMemsetAsync(B.T1.p(), 0, B.T1.bytes(), st));
+        sp_scatter_ATy(st, B.sp, x, 1.0, B.T1.p(), ld);
+        gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+        gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.W.p(), ld, 0.0, B.T3.p(), ld);
+        sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, out);
+    }
+    if (h->nlin > 0) {
+        lin_CT_y(st, h->lin, x, 1.0, 0.0, nullptr, h->tl1.p);
+        k_mul3<<<nb(h->nlin), TBK, 0, st>>>(h->nlin, h->x_lin.p, h->si_lin.p, h->tl1.p);
+        lin_C_x(st, h->lin, h->tl1.p, 1.0, out);
+    }
+}
+
+}  // namespace
+
+// =======================================================================================================================
+//  C ABI
+// =======================================================================================================================
+extern "C" {
+
+void lrn_default_options(lrn_options_t* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->kit = 0; o->datarank = 0; o->preconditioner = 1; o->erank = 1; o->aamat = 1; o->datasparsity = 8;
+    o->schur_split = 0; o->rank1_mode = 0; o->svd_tol = 0.0; o->lanczos_tol = 0.0; o->device = -1;
+}
+
+int32_t lrn_create(lrn_handle_t* out, int64_t n_var, int64_t nlmi, const int64_t* msizes, int64_t nlin,
+                   const lrn_options_t* opt) {
+    if (!out) return LRN_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LRN_ERR_NO_DEVICE;
+    lrn_solver* h = new lrn_solver();
+    if (opt) h->opt = *opt; else lrn_default_options(&h->opt);
+    int32_t rc = guarded(h, [&]() -> int32_t {
+        int dev = h->opt.device;
+        if (dev < 0) {
+            const char* lr = getenv("LOCAL_RANK");
+            dev = lr ? atoi(lr) % ndev : 0;
+        }
+        LRN_REQUIRE(dev < ndev, "device ordinal out of range");
+        h->device = dev;
+        LRN_CUDA(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        LRN_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10) {
+            h->err = "loraine_b200 requires an sm_100 (Blackwell) GPU; there is no fallback path";
+            return LRN_ERR_NO_DEVICE;
+        }
+        LRN_REQUIRE(n_var >= 1 && n_var < 65535, "n_var out of range (1..65534)");
+        LRN_REQUIRE(nlmi >= 0 && nlin >= 0 && nlin < 2000000000LL, "nlmi/nlin out of range");
+        LRN_REQUIRE(nlmi == 0 || msizes, "msizes is null");
+        h->n_var = (int)n_var; h->nlmi = (int)nlmi; h->nlin = (int)nlin;
+        LRN_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        h->blk.resize(nlmi);
+        for (int i = 0; i < nlmi; i++) {
+            LRN_REQUIRE(msizes[i] >= 1 && msizes[i] <= 46000, "block size out of range");
+            h->blk[i].m = (int)msizes[i];
+            h->sum_m += msizes[i];
+        }
+        return LRN_OK;
+    });
+    if (rc != LRN_OK && rc != LRN_ERR_NO_DEVICE) { *out = h; return rc; }
+    if (rc == LRN_ERR_NO_DEVICE) { delete h; return rc; }
+    *out = h;
+    return LRN_OK;
+}
+
+int32_t lrn_set_block_AA(lrn_handle_t h, int64_t i, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(i >= 0 && i < h->nlmi && !h->finalized, "bad block index / already finalized");
+        copy_csc(h->blk[i].hAA, (int64_t)h->blk[i].m * h->blk[i].m, colptr, rowval, nzval);
+        return LRN_OK;
+    });
+}
+int32_t lrn_set_block_C(lrn_handle_t h, int64_t i, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(i >= 0 && i < h->nlmi && !h->finalized, "bad block index / already finalized");
+        copy_csc(h->blk[i].hC, h->blk[i].m, colptr, rowval, nzval);
+        return LRN_OK;
+    });
+}
+int32_t lrn_set_block_B(lrn_handle_t h, int64_t i, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(i >= 0 && i < h->nlmi && !h->finalized, "bad block index / already finalized");
+        copy_csc(h->blk[i].hB, h->blk[i].m, colptr, rowval, nzval);
+        return LRN_OK;
+    });
+}
+int32_t lrn_set_lin(lrn_handle_t h, const int64_t* colptr, const int64_t* rowval, const double* nzval, const double* d_lin) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(!h->finalized, "already finalized");
+        if (h->nlin == 0) return LRN_OK;
+        LRN_REQUIRE(d_lin, "d_lin is null");
+        copy_csc(h->hClin, h->nlin, colptr, rowval, nzval);
+        h->d_lin.upload(d_lin, h->nlin, h->st);
+        double s = 0;
+        for (int r = 0; r < h->nlin; r++) s += d_lin[r] * d_lin[r];
+        h->normd = std::sqrt(s);
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        return LRN_OK;
+    });
+}
+int32_t lrn_set_b(lrn_handle_t h, const double* b) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(b, "b is null");
+        h->b.upload(b, h->n_var, h->st);
+        double s = 0;
+        for (int j = 0; j < h->n_var; j++) s += b[j] * b[j];
+        h->normb = std::sqrt(s);
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_finalize(lrn_handle_t h) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(!h->finalized, "already finalized");
+        LRN_REQUIRE(h->b.p, "lrn_set_b was not called");
+        const int n = h->n_var;
+        int maxm = 1;
+        for (auto& B : h->blk) { build_block(h, B); maxm = std::max(maxm, B.m); }
+        if (h->nlin > 0) {
+            LRN_REQUIRE(h->hClin.set, "lrn_set_lin was not called");
+            SparseLin& L = h->lin;
+            L.n_var = n; L.nlin = h->nlin;
+            const auto& cp = h->hClin.colptr;
+            const int64_t nnz = (int64_t)h->hClin.rowval.size();
+            L.nnz = nnz;
+            std::vector<int> cptr(cp.begin(), cp.end()), crow(h->hClin.rowval.begin(), h->hClin.rowval.end());
+            std::vector<int> rptr(n + 1, 0), rcol(nnz);
+            std::vector<double> rval(nnz);
+            for (int64_t e = 0; e < nnz; e++) {
+                LRN_REQUIRE(crow[e] >= 0 && crow[e] < n, "C_lin row index out of range");
+                rptr[crow[e] + 1]++;
+            }
+            for (int j = 0; j < n; j++) rptr[j + 1] += rptr[j];
+            std::vector<int> f(rptr.begin(), rptr.end() - 1);
+            for (int r = 0; r < h->nlin; r++)
+                for (int64_t e = cp[r]; e < cp[r + 1]; e++) {
+                    int dst = f[crow[e]]++;
+                    rcol[dst] = r; rval[dst] = h->hClin.nzval[e];
+                }
+            L.c_ptr.upload(cptr, h->st); L.c_row.upload(crow, h->st); L.c_val.upload(h->hClin.nzval, h->st);
+            L.r_ptr.upload(rptr, h->st); L.r_col.upload(rcol, h->st); L.r_val.upload(rval, h->st);
+            LRN_CUDA(cudaStreamSynchronize(h->st));
+            h->hClin = HostCSC();
+            for (auto* v : {&h->x_lin, &h->s_lin, &h->si_lin, &h->dx_lin, &h->ds_lin, &h->xn_lin, &h->sn_lin, &h->rnt_lin,
+                            &h->rd_lin, &h->tl1, &h->tl2})
+                v->alloc(h->nlin);
+        }
+        for (auto* v : {&h->y, &h->dely, &h->rhs, &h->Rp, &h->tn1, &h->tn2}) v->alloc(n);
+        const int nones = std::max(std::max(n, h->nlin), maxm);
+        h->ones.alloc(nones);
+        k_fill<<<nb(nones), TBK, 0, h->st>>>(nones, h->ones.p, 1.0);
+        h->blk_info.alloc(2 * std::max(1, h->nlmi));
+        for (int i = 0; i < h->nlmi; i++) {
+            h->blk[i].cholX.info_ext = h->blk_info.p + 2 * i;
+            h->blk[i].cholS.info_ext = h->blk_info.p + 2 * i + 1;
+        }
+        h->red.init(16 + 4 * std::max(1, h->nlmi));
+        bool rank1 = (h->opt.datarank == -1) && h->nlmi > 0;
+        for (auto& B : h->blk) rank1 = rank1 && B.sp.has_B;
+        if (h->opt.datarank == -1 && !rank1) h->opt.datarank = 0;      // src/Solvers.jl:435-444
+        if (h->opt.kit == 0) {
+            h->H.init(n, n);
+            h->L.init(n, n);
+            if (rank1) h->BG.init(n, maxm);
+        }
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        h->finalized = true;
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_destroy(lrn_handle_t h) {
+    if (!h) return LRN_OK;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : h->evpool) cudaEventDestroy(e);
+    cudaStream_t st = h->st;
+    delete h;
+    if (st) cudaStreamDestroy(st);
+    return LRN_OK;
+}
+
+const char* lrn_last_error(lrn_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+// ---- iterate ----------------------------------------------------------------------------------------------------------
+int32_t lrn_set_iterate(lrn_handle_t h, const double* const* X, const double* const* S, const double* y, const double* x_lin,
+                        const double* s_lin) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(h->finalized, "lrn_finalize first");
+        for (int i = 0; i < h->nlmi; i++) {
+            LRN_REQUIRE(X && S && X[i] && S[i], "null X/S block");
+            upload_dense(h, h->blk[i].X, X[i]);
+            upload_dense(h, h->blk[i].S, S[i]);
+            h->blk[i].chol_cached = false;
+        }
+        LRN_REQUIRE(y, "null y");
+        h->y.upload(y, h->n_var, h->st);
+        if (h->nlin > 0) {
+            LRN_REQUIRE(x_lin && s_lin, "null x_lin/s_lin");
+            h->x_lin.upload(x_lin, h->nlin, h->st);
+            h->s_lin.upload(s_lin, h->nlin, h->st);
+            vec_op(h->st, h->nlin, VEC_RECIP, h->si_lin.p, h->s_lin.p, nullptr);
+        }
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        h->have_factor = false;
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_get_solution(lrn_handle_t h, double* y, double* const* X, double* x_lin) {
+    return guarded(h, [&]() -> int32_t {
+        if (y) LRN_CUDA(cudaMemcpyAsync(y, h->y.p, h->n_var * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        if (X)
+            for (int i = 0; i < h->nlmi; i++)
+                if (X[i]) download_dense(h, h->blk[i].X.p(), h->blk[i].ld, h->blk[i].m, h->blk[i].m, X[i]);
+        if (x_lin && h->nlin > 0)
+            LRN_CUDA(cudaMemcpyAsync(x_lin, h->x_lin.p, h->nlin * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_get_slack(lrn_handle_t h, double* const* S, double* s_lin) {
+    return guarded(h, [&]() -> int32_t {
+        if (S)
+            for (int i = 0; i < h->nlmi; i++)
+                if (S[i]) download_dense(h, h->blk[i].S.p(), h->blk[i].ld, h->blk[i].m, h->blk[i].m, S[i]);
+        if (s_lin && h->nlin > 0)
+            LRN_CUDA(cudaMemcpyAsync(s_lin, h->s_lin.p, h->nlin * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        return LRN_OK;
+    });
+}
+
+// ---- hot path -------------------------------------------------------------------------------------------------------
+int32_t lrn_find_mu(lrn_handle_t h, double* mu) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(mu, "null output");
+        cudaStream_t st = h->st;
+        h->red.zero(st);
+        for (auto& B : h->blk) h->red.dot_mat(st, B.m, B.m, B.X.p(), B.ld, B.S.p(), B.ld, 0, true);
+        if (h->nlin > 0) h->red.dot_vec(st, h->nlin, h->x_lin.p, h->s_lin.p, 0, true);
+        const double* r = h->red.fetch(st);
+        *mu = r[0] / (double)(h->sum_m + h->nlin);
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
+    return guarded(h, [&]() -> int32_t {
+        Phase ph(h, LRN_T_PREPARE_W);
+        cudaStream_t st = h->st;
+        if (status4) *status4 = 0;
+        const double svd_tol = h->opt.svd_tol > 0 ? h->opt.svd_tol : 1e-9;
+        for (auto& B : h->blk) {
+            const int m = B.m, ld = B.ld;
+            if (!B.chol_cached) {
+                bool okx = try_cholesky(h, B.X, B.LX, B.cholX);
+                bool oks = try_cholesky(h, B.S, B.LS, B.cholS);
+                if ((!okx || !oks) && status4) *status4 = 1;
+            }
+            B.chol_cached = false;
+            zero_strict_upper(B.LX.p(), m, ld, st);
+            zero_strict_upper(B.LS.p(), m, ld, st);
+            // CC = L_S' L_X                                                   (src/prepare_W.jl:39)
+            gemm_tn(st, m, m, m, 1.0, B.LS.p(), ld, B.LX.p(), ld, 0.0, B.T1.p(), ld);
+            // U*D, V, D = svd(CC)                                             (src/prepare_W.jl:42)
+            {
+                Phase ps(h, LRN_T_SVD);
+                h->stat_svd_sweeps = svd_block_jacobi(B.T1.p(), ld, m, B.T2.p(), ld, B.T3.p(), ld, B.D.p, B.svd, svd_tol, 30, st);
+            }
+            vec_op(st, m, VEC_RSQRT, B.dm12.p, B.D.p, nullptr);
+            vec_op(st, m, VEC_POW_M32, B.dm32.p, B.D.p, nullptr);
+            // G = L_X V D^{-1/2}                                              (src/prepare_W.jl:60)
+            {
+                GemmParams p;
+                p.A = B.LX.p(); p.B = B.T3.p(); p.C = B.G.p(); p.M = m; p.N = m; p.K = m; p.lda = ld; p.ldb = ld; p.ldc = ld;
+                p.colscale = B.dm12.p;
+                gemm(p, st);
+            }
+            // Gi = inv(G) = D^{-1/2} U' L_S' = (L_S (U D) D^{-3/2})'          (src/prepare_W.jl:63, closed form)
+            {
+                GemmParams p;
+                p.A = B.LS.p(); p.B = B.T2.p(); p.C = B.T1.p(); p.M = m; p.N = m; p.K = m; p.lda = ld; p.ldb = ld; p.ldc = ld;
+                p.colscale = B.dm32.p;
+                gemm(p, st);
+                mat_transpose(st, m, B.Gi.p(), ld, B.T1.p(), ld);
+            }
+            // W = G G'                                                        (src/prepare_W.jl:64)
+            gemm_nt(st, m, m, m, 1.0, B.G.p(), ld, B.G.p(), ld, 0.0, B.W.p(), ld);
+            mat_symmetrize(st, m, B.W.p(), ld);
+            // Si = S^{-1} = (G D^{-1/2}) (G D^{-1/2})'                        (src/prepare_W.jl:68; G'SG = D)
+            mat_scale_cols(st, m, m, B.T1.p(), ld, B.G.p(), ld, B.dm12.p);
+            gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.T1.p(), ld, 0.0, B.Si.p(), ld);
+            mat_symmetrize(st, m, B.Si.p(), ld);
+            // DDsi = 1 ./ sqrt(diag(G' S G))                                  (src/prepare_W.jl:71-74)
+            gemm_nn(st, m, m, m, 1.0, B.S.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+            mat_coldot(st, m, m, B.G.p(), ld, B.T1.p(), ld, B.vtmp.p);
+            vec_op(st, m, VEC_RSQRT, B.DDsi.p, B.vtmp.p, nullptr);
+        }
+        if (h->nlin > 0) vec_op(st, h->nlin, VEC_RECIP, h->si_lin.p, h->s_lin.p, nullptr);
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_residuals(lrn_handle_t h) {
+    return guarded(h, [&]() -> int32_t {
+        Phase ph(h, LRN_T_RESIDUALS);
+        cudaStream_t st = h->st;
+        const int n = h->n_var;
+        LRN_CUDA(cudaMemcpyAsync(h->Rp.p, h->b.p, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (auto& B : h->blk) {
+            sp_A_vec(st, B.sp, B.X.p(), B.ld, -1.0, h->Rp.p);
+            mat_lincomb(st, B.m, B.m, B.Rd.p(), B.ld, 1.0, B.C.p(), B.C.ld, -1.0, B.S.p(), B.ld, 0.0, nullptr, 0);
+            sp_scatter_ATy(st, B.sp, h->y.p, -1.0, B.Rd.p(), B.ld);
+        }
+        if (h->nlin > 0) {
+            lin_C_x(st, h->lin, h->x_lin.p, -1.0, h->Rp.p);
+            vec_axpby(st, h->nlin, h->tl1.p, 1.0, h->d_lin.p, -1.0, h->s_lin.p);
+            lin_CT_y(st, h->lin, h->y.p, -1.0, 1.0, h->tl1.p, h->rd_lin.p);
+        }
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_schur_assemble(lrn_handle_t h) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
+        Phase ph(h, LRN_T_ASSEMBLE);
+        cudaStream_t st = h->st;
+        const int n = h->n_var;
+        LRN_CUDA(cudaMemsetAsync(h->H.p(), 0, h->H.bytes(), st));
+        for (auto& B : h->blk) {
+            const int m = B.m, ld = B.ld;
+            if (h->opt.datarank == -1) {
+                // BBBB += ((B G)(B G)').^2                                    (src/makeBBBB.jl:7-14)
+                sp_B_times_G(st, B.sp, B.G.p(), ld, h->BG.p(), h->BG.ld);
+                GemmParams p;
+                p.A = h->BG.p(); p.B = h->BG.p(); p.C = h->H.p();
+                p.M = n; p.N = n; p.K = m; p.lda = h->BG.ld; p.ldb = h->BG.ld; p.ldc = h->H.ld;
+                p.transB = true; p.alpha = 1.0; p.beta = 1.0; p.mode = 1; p.lower = 1;
+                gemm(p, st);
+            } else {
+                for (int jj = 0; jj < B.sp.nF1; jj++) {
+                    // F1: U = W calA_j W, column of <calA_k, U>                (src/makeBBBB.jl:81-104)
+                    LRN_CUDA(cudaMemsetAsync(B.T1.p(), 0, B.T1.bytes(), st));
+                    sp_densify(st, B.sp, B.sp.h_part[jj], B.T1.p(), ld);
+                    gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+                    gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.W.p(), ld, 0.0, B.T3.p(), ld);
+                    sp_schur_f1_column(st, B.sp, jj, B.T3.p(), ld, h->H.p(), h->H.ld);
+                }
+                // F3 for the remaining (sparse) matrices                       (src/makeBBBB.jl:139-213)
+                sp_schur_pairs(st, B.sp, B.sp.nF1, B.W.p(), ld, h->H.p(), h->H.ld);
+            }
+        }
+        if (h->nlin > 0) {
+            // BBBB += C_lin * spdiagm(X_lin .* S_lin_inv) * C_lin'             (src/predictor_corrector.jl:36-38)
+            vec_op(st, h->nlin, VEC_MUL, h->tl1.p, h->x_lin.p, h->si_lin.p);
+            lin_schur(st, h->lin, h->tl1.p, h->H.p(), h->H.ld);
+        }
+        h->have_factor = false;
+        return LRN_OK;
+    });
+}
+
+static void add_lp_rhs(lrn_solver* h, int corr, double sigmamu) {
+    if (h->nlin <= 0) return;
+    k_lp_rhs<<<nb(h->nlin), TBK, 0, h->st>>>(h->nlin, corr, sigmamu, h->x_lin.p, h->si_lin.p, h->rd_lin.p, h->dx_lin.p,
+                                              h->ds_lin.p, h->tl1.p);
+    lin_C_x(h->st, h->lin, h->tl1.p, 1.0, h->rhs.p);
+}
+
+int32_t lrn_rhs_predictor(lrn_handle_t h) {
+    return guarded(h, [&]() -> int32_t {
+        Phase ph(h, LRN_T_RHS);
+        cudaStream_t st = h->st;
+        LRN_CUDA(cudaMemcpyAsync(h->rhs.p, h->Rp.p, h->n_var * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (auto& B : h->blk) {
+            const int m = B.m, ld = B.ld;
+            // h += AA * vec(W (Rd + S) W)                                     (src/makeBBBB.jl:225)
+            mat_lincomb(st, m, m, B.T1.p(), ld, 1.0, B.Rd.p(), ld, 1.0, B.S.p(), ld, 0.0, nullptr, 0);
+            gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+            gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.W.p(), ld, 0.0, B.T3.p(), ld);
+            sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
+        }
+        add_lp_rhs(h, 0, 0.0);
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
+    return guarded(h, [&]() -> int32_t {
+        Phase ph(h, LRN_T_RHS);
+        cudaStream_t st = h->st;
+        const double sm = sigma * mu;
+        LRN_CUDA(cudaMemcpyAsync(h->rhs.p, h->Rp.p, h->n_var * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (auto& B : h->blk) {
+            const int m = B.m, ld = B.ld;
+            // h += AA * vec(G (G' Rd G + diag(D) - diag(sigma mu ./ D) - RNT) G')      (src/predictor_corrector.jl:186)
+            gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+            gemm_tn(st, m, m, m, 1.0, B.G.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+            mat_corr_inner(st, m, B.T2.p(), ld, B.D.p, sm, B.RNT.p(), ld);
+            gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.T2.p(), ld, 0.0, B.T1.p(), ld);
+            gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.G.p(), ld, 0.0, B.T3.p(), ld);
+            sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
+        }
+        add_lp_rhs(h, 1, sm);
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_schur_factor(lrn_handle_t h) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
+        int info = 0;
+        {
+            Phase ph(h, LRN_T_FACTOR);
+            cudaStream_t st = h->st;
+            LRN_CUDA(cudaMemcpyAsync(h->L.p(), h->H.p(), h->H.bytes(), cudaMemcpyDeviceToDevice, st));
+            cholesky_lower(h->L.p(), h->n_var, h->L.ld, h->cholH, st);
+            LRN_CUDA(cudaMemcpyAsync(&info, h->cholH.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
+            LRN_CUDA(cudaStreamSynchronize(st));
+        }
+        h->have_factor = (info == 0);
+        return info;
+    });
+}
+
+int32_t lrn_schur_shift(lrn_handle_t h, double delta) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
+        mat_add_diag(h->st, h->n_var, h->H.p(), h->H.ld, delta);
+        h->have_factor = false;
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_schur_solve(lrn_handle_t h, int32_t which) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(h->have_factor, "no valid Cholesky factor (call lrn_schur_factor)");
+        LRN_REQUIRE(which == 1 || which == 2 || which == 3 || which == 6, "which must be 1, 2, 3 or 6");
+        Phase ph(h, LRN_T_SOLVE);
+        cudaStream_t st = h->st;
+        LRN_CUDA(cudaMemcpyAsync(h->dely.p, h->rhs.p, h->n_var * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        const int reps = (which == 6) ? 2 : 1;
+        const int w = (which == 6) ? 3 : which;
+        for (int r = 0; r < reps; r++) chol_solve(h->L.p(), h->n_var, h->L.ld, h->cholH, h->dely.p, h->tn1.p, w, st);
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, double tau, double* alpha, double* beta,
+                      double* alpha_lin, double* beta_lin) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE((h->nlmi == 0 || (alpha && beta)) && alpha_lin && beta_lin, "null outputs");
+        Phase ph(h, LRN_T_FIND_STEP);
+        cudaStream_t st = h->st;
+        const double sm = sigma * mu;
+        for (int i = 0; i < h->nlmi; i++) {
+            Block& B = h->blk[i];
+            const int m = B.m, ld = B.ld;
+            // delS = Rd - mat(AA' dely)                                        (src/predictor_corrector.jl:252)
+            LRN_CUDA(cudaMemcpyAsync(B.dS.p(), B.Rd.p(), B.Rd.bytes(), cudaMemcpyDeviceToDevice, st));
+            sp_scatter_ATy(st, B.sp, h->dely.p, -1.0, B.dS.p(), ld);
+            // Xi = W delS W                                                    (:253)
+            gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.dS.p(), ld, 0.0, B.T1.p(), ld);
+            gemm_nn(st, m, m, m, 1.0, B.T1.p(), ld, B.W.p(), ld, 0.0, B.T2.p(), ld);
+            if (predict) {
+                // delX = mat(-X - Xi)                                          (:255)
+                mat_sym_lincomb(st, m, B.dX.p(), ld, -1.0, B.X.p(), ld, -1.0, B.T2.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
+            } else {
+                // delX = mat(sigma mu Si - X - Xi + G RNT G')                  (:257)
+                gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.RNT.p(), ld, 0.0, B.T1.p(), ld);
+                gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.G.p(), ld, 0.0, B.T3.p(), ld);
+                mat_sym_lincomb(st, m, B.dX.p(), ld, sm, B.Si.p(), ld, -1.0, B.X.p(), ld, -1.0, B.T2.p(), ld, 1.0, B.T3.p(), ld);
+            }
+            // delXb = Gi delX Gi' ; XXX = sym(DDsi' .* delXb .* DDsi) ; eigmin  (:264,:268-272)
+            gemm_nt(st, m, m, m, 1.0, B.dX.p(), ld, B.Gi.p(), ld, 0.0, B.T1.p(), ld);
+            gemm_nn(st, m, m, m, 1.0, B.Gi.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+            mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
+            alpha[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
+            // delSb = G' delS G                                                (:263,:281-285)
+            gemm_nn(st, m, m, m, 1.0, B.dS.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+            gemm_tn(st, m, m, m, 1.0, B.G.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+            mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
+            beta[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
+        }
+        *alpha_lin = 1.0;
+        *beta_lin = 1.0;
+        if (h->nlin > 0) {
+            // find_step_lin                                                    (:329-347)
+            const int nl = h->nlin;
+            lin_CT_y(st, h->lin, h->dely.p, -1.0, 1.0, h->rd_lin.p, h->ds_lin.p);
+            k_lp_dx<<<nb(nl), TBK, 0, st>>>(nl, predict ? 0 : 1, sm, h->x_lin.p, h->si_lin.p, h->ds_lin.p, h->rnt_lin.p, h->dx_lin.p);
+            h->red.min_ratio(st, nl, h->dx_lin.p, h->x_lin.p, 0, false);
+            h->red.min_ratio(st, nl, h->ds_lin.p, h->s_lin.p, 1, false);
+            const double* r = h->red.fetch(st);
+            *alpha_lin = steplen(r[0], tau);
+            *beta_lin = steplen(r[1], tau);
+        }
+        if (predict) {
+            for (int i = 0; i < h->nlmi; i++) {
+                Block& B = h->blk[i];
+                const int m = B.m, ld = B.ld;
+                // Xn, Sn, RNT                                                   (:306-309)
+                mat_lincomb(st, m, m, B.Xn.p(), ld, 1.0, B.X.p(), ld, alpha[i], B.dX.p(), ld, 0.0, nullptr, 0);
+                mat_lincomb(st, m, m, B.Sn.p(), ld, 1.0, B.S.p(), ld, beta[i], B.dS.p(), ld, 0.0, nullptr, 0);
+                gemm_nn(st, m, m, m, 1.0, B.dX.p(), ld, B.dS.p(), ld, 0.0, B.T1.p(), ld);
+                gemm_nn(st, m, m, m, 1.0, B.Gi.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+                gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.G.p(), ld, 0.0, B.T3.p(), ld);
+                mat_rnt(st, m, B.RNT.p(), ld, B.T3.p(), ld, B.D.p);
+            }
+            if (h->nlin > 0)
+                k_lp_pred_update<<<nb(h->nlin), TBK, 0, st>>>(h->nlin, *alpha_lin, *beta_lin, h->x_lin.p, h->s_lin.p, h->dx_lin.p,
+                                                              h->ds_lin.p, h->si_lin.p, h->xn_lin.p, h->sn_lin.p, h->rnt_lin.p);
+        } else {
+            double amin = *alpha_lin, bmin = *beta_lin;
+            for (int i = 0; i < h->nlmi; i++) { amin = std::min(amin, alpha[i]); bmin = std::min(bmin, beta[i]); }
+            // y, X, S update                                                    (:313-321, :358-360)
+            vec_axpby(st, h->n_var, h->y.p, 1.0, h->y.p, bmin, h->dely.p);
+            for (auto& B : h->blk) {
+                const int m = B.m, ld = B.ld;
+                mat_lincomb(st, m, m, B.X.p(), ld, 1.0, B.X.p(), ld, amin, B.dX.p(), ld, 0.0, nullptr, 0);
+                mat_symmetrize(st, m, B.X.p(), ld);
+                mat_lincomb(st, m, m, B.S.p(), ld, 1.0, B.S.p(), ld, bmin, B.dS.p(), ld, 0.0, nullptr, 0);
+                mat_symmetrize(st, m, B.S.p(), ld);
+                B.chol_cached = false;
+            }
+            if (h->nlin > 0) {
+                vec_axpby(st, h->nlin, h->x_lin.p, 1.0, h->x_lin.p, amin, h->dx_lin.p);
+                vec_axpby(st, h->nlin, h->s_lin.p, 1.0, h->s_lin.p, bmin, h->ds_lin.p);
+                // S_lin_inv is refreshed; Si_lin (same values) is refreshed by the next prepare_W like in the reference
+                vec_op(st, h->nlin, VEC_RECIP, h->si_lin.p, h->s_lin.p, nullptr);
+            }
+        }
+        LRN_CUDA(cudaStreamSynchronize(st));
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_sigma_trace(lrn_handle_t h, double* tr, double* dl) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(tr && dl, "null outputs");
+        cudaStream_t st = h->st;
+        h->red.zero(st);
+        for (auto& B : h->blk) h->red.dot_mat(st, B.m, B.m, B.Xn.p(), B.ld, B.Sn.p(), B.ld, 0, true);
+        if (h->nlin > 0) h->red.dot_vec(st, h->nlin, h->xn_lin.p, h->sn_lin.p, 1, false);
+        const double* r = h->red.fetch(st);
+        *tr = r[0];
+        *dl = r[1];
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_dimacs(lrn_handle_t h, double* err6, double* by_out, double* trCX_out, double* dx_out) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(err6, "null output");
+        Phase ph(h, LRN_T_DIMACS);
+        cudaStream_t st = h->st;
+        Reducer& R = h->red;
+        R.zero(st);
+        // slots: 0 Rp.Rp, 1 b.y, 2 min x_lin, 3 rd_lin.rd_lin, 4 min s_lin, 5 d.x, 6 s.x ; per block 16+4i: Rd.Rd, S.X, C.X
+        R.dot_vec(st, h->n_var, h->Rp.p, h->Rp.p, 0, false);
+        R.dot_vec(st, h->n_var, h->b.p, h->y.p, 1, false);
+        for (int i = 0; i < h->nlmi; i++) {
+            Block& B = h->blk[i];
+            R.dot_mat(st, B.m, B.m, B.Rd.p(), B.ld, B.Rd.p(), B.ld, 16 + 4 * i, false);
+            R.dot_mat(st, B.m, B.m, B.S.p(), B.ld, B.X.p(), B.ld, 16 + 4 * i + 1, false);
+            R.dot_mat(st, B.m, B.m, B.C.p(), B.C.ld, B.X.p(), B.ld, 16 + 4 * i + 2, false);
+            // eigmin(X), eigmin(S) only enter as max(0, -eigmin): a successful Cholesky proves eigmin > 0; the factors
+            // are kept for the next prepare_W (X and S do not change in between)
+            LRN_CUDA(cudaMemcpyAsync(B.LX.p(), B.X.p(), B.X.bytes(), cudaMemcpyDeviceToDevice, st));
+            cholesky_lower(B.LX.p(), B.m, B.ld, B.cholX, st);
+            LRN_CUDA(cudaMemcpyAsync(B.LS.p(), B.S.p(), B.S.bytes(), cudaMemcpyDeviceToDevice, st));
+            cholesky_lower(B.LS.p(), B.m, B.ld, B.cholS, st);
+        }
+        if (h->nlin > 0) {
+            R.min_ratio(st, h->nlin, h->x_lin.p, nullptr, 2, false);
+            R.dot_vec(st, h->nlin, h->rd_lin.p, h->rd_lin.p, 3, false);
+            R.min_ratio(st, h->nlin, h->s_lin.p, nullptr, 4, false);
+            R.dot_vec(st, h->nlin, h->d_lin.p, h->x_lin.p, 5, false);
+            R.dot_vec(st, h->nlin, h->s_lin.p, h->x_lin.p, 6, false);
+        }
+        std::vector<int> infos(2 * std::max(1, h->nlmi), 0);
+        if (h->nlmi > 0)
+            LRN_CUDA(cudaMemcpyAsync(infos.data(), h->blk_info.p, 2 * h->nlmi * sizeof(int), cudaMemcpyDeviceToHost, st));
+        const double* r = R.fetch(st);
+        std::vector<double> v(r, r + R.nslots);
+        const double nb_ = h->normb, by = v[1];
+        double e1 = std::sqrt(v[0]) / (1 + nb_), e2 = 0, e3 = 0, e4 = 0, e5 = 0, e6 = 0, trCX = 0;
+        for (int i = 0; i < h->nlmi; i++) {
+            Block& B = h->blk[i];
+            const double CX = v[16 + 4 * i + 2];
+            trCX += CX;
+            double lx = 1.0, ls = 1.0;
+            if (infos[2 * i] != 0) lx = lambda_min(h, B.X.p(), B.m, B.ld);
+            if (infos[2 * i + 1] != 0) ls = lambda_min(h, B.S.p(), B.m, B.ld);
+            B.chol_cached = (infos[2 * i] == 0 && infos[2 * i + 1] == 0);
+            e2 += std::max(0.0, -lx / (1 + nb_));
+            e3 += std::sqrt(v[16 + 4 * i]) / (1 + B.normC);
+            e4 += std::max(0.0, -ls / (1 + B.normC));
+            e6 += v[16 + 4 * i + 1] / (1 + std::fabs(CX) + std::fabs(by));
+        }
+        e5 = (trCX - by) / (1 + std::fabs(trCX) + std::fabs(by));
+        double dx = 0.0;
+        if (h->nlin > 0) {
+            dx = v[5];
+            e2 += std::max(0.0, -v[2] / (1 + nb_));
+            e3 += std::sqrt(v[3]) / (1 + h->normd);
+            e4 += std::max(0.0, -v[4] / (1 + h->normd));
+            e5 = (trCX + dx - by) / (1 + std::fabs(trCX) + std::fabs(by));
+            e6 += v[6] / (1 + std::fabs(dx) + std::fabs(by));
+        }
+        err6[0] = e1; err6[1] = e2; err6[2] = e3; err6[3] = e4; err6[4] = e5; err6[5] = e6;
+        if (by_out) *by_out = by;
+        if (trCX_out) *trCX_out = trCX;
+        if (dx_out) *dx_out = dx;
+        return LRN_OK;
+    });
+}
+
+// ---- parity hooks -------------------------------------------------------------------------------------------------------
+int32_t lrn_get_array(lrn_handle_t h, int32_t which, int64_t iblk, double* out) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(out, "null output");
+        cudaStream_t st = h->st;
+        const int n = h->n_var;
+        auto vec_out = [&](const double* p, int len) {
+            LRN_CUDA(cudaMemcpyAsync(out, p, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, st));
+        };
+        if (which == LRN_ARR_H || which == LRN_ARR_L) {
+            LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
+            DMat& M = (which == LRN_ARR_H) ? h->H : h->L;
+            // work on a copy in tn-sized chunks is not possible: use the spare matrix of the other kind only when safe
+            if (which == LRN_ARR_H) mat_mirror_lower(st, n, M.p(), M.ld);
+            else zero_strict_upper(M.p(), n, M.ld, st);
+            download_dense(h, M.p(), M.ld, n, n, out);
+        } else if (which == LRN_ARR_RHS) vec_out(h->rhs.p, n);
+        else if (which == LRN_ARR_DELY) vec_out(h->dely.p, n);
+        else if (which == LRN_ARR_RP) vec_out(h->Rp.p, n);
+        else {
+            LRN_REQUIRE(iblk >= 0 && iblk < h->nlmi, "bad block index");
+            Block& B = h->blk[iblk];
+            const DMat* M = nullptr;
+            switch (which) {
+                case LRN_ARR_W: M = &B.W; break;
+                case LRN_ARR_G: M = &B.G; break;
+                case LRN_ARR_GI: M = &B.Gi; break;
+                case LRN_ARR_SI: M = &B.Si; break;
+                case LRN_ARR_RD: M = &B.Rd; break;
+                case LRN_ARR_DELX: M = &B.dX; break;
+                case LRN_ARR_DELS: M = &B.dS; break;
+                case LRN_ARR_RNT: M = &B.RNT; break;
+                case LRN_ARR_XN: M = &B.Xn; break;
+                case LRN_ARR_SN: M = &B.Sn; break;
+                case LRN_ARR_D: vec_out(B.D.p, B.m); break;
+                case LRN_ARR_DDSI: vec_out(B.DDsi.p, B.m); break;
+                default: LRN_REQUIRE(false, "unknown array id");
+            }
+            if (M) download_dense(h, M->p(), M->ld, B.m, B.m, out);
+        }
+        LRN_CUDA(cudaStreamSynchronize(st));
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_timers(lrn_handle_t h, double* ms, int64_t* calls, int32_t reset) {
+    return guarded(h, [&]() -> int32_t {
+        flush_timers(h);
+        for (int i = 0; i < LRN_T_COUNT; i++) {
+            if (ms) ms[i] = h->t_ms[i];
+            if (calls) calls[i] = h->t_calls[i];
+            if (reset) { h->t_ms[i] = 0; h->t_calls[i] = 0; }
+        }
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(name, "null name");
+        std::string n(name);
+        if (n == "aamat") h->opt.aamat = (int)value;
+        else if (n == "erank") { LRN_REQUIRE(h->prec_ready == 0, "erank cannot change after a preconditioner was built"); h->opt.erank = (int)value; }
+        else if (n == "svd_tol") h->opt.svd_tol = value;
+        else if (n == "lanczos_tol") h->opt.lanczos_tol = value;
+        else LRN_REQUIRE(false, "unknown option name");
+        return LRN_OK;
+    });
+}
+
+int64_t lrn_kernel_launches(void) { return (int64_t)lrn::g_kernel_launches.load(); }
+
+int32_t lrn_stats(lrn_handle_t h, int64_t* out3) {
+    return guarded(h, [&]() -> int32_t {
+        LRN_REQUIRE(out3, "null output");
+        out3[0] = h->stat_svd_sweeps; out3[1] = h->stat_lanczos_iters; out3[2] = h->stat_lanczos_fail;
+        return LRN_OK;
+    });
+}
+
+}  // extern "C"
+
+// The CG / preconditioner entry points live in pcg.cu; they use apply_A through this hook.
+namespace lrn {
+void solver_apply_A(lrn_solver* h, const double* x, double* out) { apply_A(h, x, out); }
+void solver_flush_timers(lrn_solver* h) { flush_timers(h); }
+}  // namespace lrn

@@ -1,0 +1,83 @@
+// Device-resident solver state behind the opaque C handle (mirrors MySolver / MyModel / Halpha of the reference,
+// src/Solvers.jl:18-162, src/model.jl:34-87, but as typed, pre-allocated device buffers).
+#pragma once
+#include "../../include/loraine_b200.h"
+#include "chol.cuh"
+#include "common.cuh"
+#include "eig.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace lrn {
+
+struct HostCSC {                       // staging copy of a Julia SparseMatrixCSC (converted to 0-based)
+    std::vector<int64_t> colptr;
+    std::vector<int64_t> rowval;
+    std::vector<double> nzval;
+    bool set = false;
+};
+
+struct Block {
+    int m = 0, ld = 0;
+    HostCSC hAA, hB, hC;               // released after finalize
+    SparseBlock sp;
+    DMat C;
+    double normC = 0.0;
+    DMat X, S, dX, dS, Xn, Sn, G, Gi, W, Si, Rd, RNT, LX, LS, T1, T2, T3;
+    DevBuf<double> D, DDsi, dm12, dm32, vtmp;
+    CholWork cholX, cholS;
+    SvdWork svd;
+    bool chol_cached = false;
+    // H_alpha preconditioner pieces (src/Solvers.jl:149-162 Halpha)
+    DMat U, Zf, MU, ZY;                // U m x erank ; Z = chol(2 W0 + U U') lower ; work m x erank
+    double tau = 0.0;
+};
+
+struct PhaseEvt {
+    cudaEvent_t a, b;
+    int phase;
+};
+
+}  // namespace lrn
+
+struct lrn_solver {
+    lrn_options_t opt;
+    int device = 0;
+    int n_var = 0, nlmi = 0, nlin = 0;
+    long long sum_m = 0;
+    bool finalized = false;
+    std::vector<lrn::Block> blk;
+    lrn::HostCSC hClin;
+    lrn::SparseLin lin;
+    lrn::DevBuf<double> b, d_lin, y, dely, rhs, Rp, tn1, tn2, ones;
+    lrn::DevBuf<double> x_lin, s_lin, si_lin, dx_lin, ds_lin, xn_lin, sn_lin, rnt_lin, rd_lin, tl1, tl2;
+    double normb = 0.0, normd = 0.0;
+    lrn::DMat H, L, BG;
+    lrn::CholWork cholH;
+    bool have_factor = false;
+    lrn::DevBuf<int> blk_info;         // 2 per block (chol X, chol S)
+    lrn::Reducer red;
+    lrn::LanczosWork lan;
+    cudaStream_t st = nullptr;
+    std::string err;
+    // timers
+    std::vector<lrn::PhaseEvt> pending;
+    std::vector<cudaEvent_t> evpool;
+    double t_ms[LRN_T_COUNT] = {0};
+    long long t_calls[LRN_T_COUNT] = {0};
+    long long stat_svd_sweeps = 0, stat_lanczos_iters = 0, stat_lanczos_fail = 0;
+    // CG / preconditioner state
+    lrn::DevBuf<double> cg_r, cg_z, cg_p, cg_Ap, cg_scal;
+    lrn::DevBuf<double> pDiag, pDsq, pT, pS, pY, pAU;
+    lrn::DMat pDd;                     // dense AAAATtau when nlin > 0
+    lrn::CholWork cholS, cholD;
+    bool pDense = false;
+    int kS = 0;
+    int prec_ready = 0;                // kind prepared (0 none)
+    // distributed
+    int rank = 0, world = 1;
+    void* nccl = nullptr;
+};

@@ -1,0 +1,260 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on the same inputs, function by function
+and end to end, plus the committed golden fixtures and the reference's known answers."""
+import os
+
+import numpy as np
+import pytest
+
+import jump_examples as je
+
+pytestmark = pytest.mark.gpu
+
+OPTS_SDPA = dict(kit=0, tol_cg=1e-2, tol_cg_min=1e-6, eDIMACS=1e-6, preconditioner=1, erank=1, aamat=2, verb=0, datarank=0,
+                 initpoint=1, maxit=100, datasparsity=8)
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+def golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    return z, (int(z["n"]), [int(b) for b in z["bs"]], z["c"], z["body"])
+
+
+def make_pair(pkg, arrays, opts):
+    """the same problem prepared for the CUDA path and for the oracle"""
+    from oracle import loraine_oracle as lo, sdpa_io
+    opt = pkg.Optimizer()
+    for k, v in opts.items():
+        opt.set_attribute(k, v)
+    if isinstance(arrays, dict):
+        opt.copy_to(pkg.RawProblem(**je.fields(arrays)), max_sense=arrays["max_sense"])
+        oraw = sdpa_io.RawProblem(**je.fields(arrays))
+    else:
+        opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+        oraw = sdpa_io.raw_from_sdpa_arrays(*arrays)
+    o = dict(lo.DEFAULT_OPTIONS)
+    o.update(opts)
+    md = lo.prepare_model(oraw, datarank=int(o["datarank"]), kappa=int(o["datasparsity"]))
+    s, ha = lo.load(md, o)
+    return opt, (lo, s, ha)
+
+
+def step_both(pkg, opt, ora, iters):
+    """run `iters` full IP iterations on both sides"""
+    from loraine_jl_b200 import solver as S
+    lo, s, ha = ora
+    g = opt.solver
+    S.setup_solver(g, opt.halpha)
+    S.initial_point(g)
+    lo.setup_solver(s, ha)
+    lo.initial_point(s)
+    for _ in range(iters):
+        S.myIPstep(g, opt.halpha)
+        g.itertime = 0.0
+        g.tol_cg = max(g.tol_cg * g.tol_cg_up, g.tol_cg_min)
+        S.check_convergence(g)
+        lo.myIPstep(s, ha)
+        s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
+        lo.check_convergence(s)
+    return g, s
+
+
+@pytest.mark.parametrize("name,nblk", [("theta1", 1), ("control1", 2), ("vib3", 2)])
+def test_first_iterations_match_oracle(pkg, golden_dir, name, nblk):
+    z, arrays = golden(golden_dir, name)
+    opt, ora = make_pair(pkg, arrays, OPTS_SDPA)
+    g, s = step_both(pkg, opt, ora, 3)
+    # the fourth iteration is compared phase by phase
+    from loraine_jl_b200 import solver as S
+    lo = ora[0]
+    for side, mod, st, ha in ((0, S, g, opt.halpha), (1, lo, s, ora[2])):
+        st.iter += 1
+        st.cg_iter_pre = st.cg_iter_cor = 0
+        mod.find_mu(st)
+        mod.prepare_W(st)
+    assert abs(g.mu - s.mu) <= 1e-10 * abs(s.mu)
+    for i in range(nblk):
+        assert relerr(g.get_array("W", i), s.W[i]) <= 1e-9                 # W is unique (W S W = X)
+        assert relerr(np.sort(g.get_array("D", i)), np.sort(s.D[i])) <= 1e-9
+        Gg, Gig = g.get_array("G", i), g.get_array("GI", i)
+        m = Gg.shape[0]
+        assert np.linalg.norm(Gg @ Gig - np.eye(m)) <= 1e-7 * m            # Gi = inv(G) in closed form
+        assert relerr(g.get_array("SI", i), s.Si[i]) <= 1e-8
+    S.predictor(g, opt.halpha)
+    lo.predictor(s, ora[2])
+    H = g.get_array("H")
+    got = []
+    s.hooks["H"] = lambda s_, Hm: got.append(Hm.copy())
+    # oracle H of the same iterate (recompute from the oracle's W)
+    Ho = lo.makeBBBBs(s.model, s.W)
+    if s.model.nlin > 0:
+        Ho = Ho + lo.lp_schur(s.model, s.X_lin * s.S_lin_inv)
+    assert relerr(H, Ho) <= 1e-9                                           # oracle W differs by its own SVD rounding
+    assert relerr(g.get_array("DELY"), s.dely) <= 1e-7
+    assert np.allclose(g.alpha, s.alpha, rtol=1e-6) and np.allclose(g.beta, s.beta, rtol=1e-6)
+    assert abs(S.sigma_update(g) - lo.sigma_update(s)) <= 1e-6
+    S.corrector(g, opt.halpha)
+    lo.corrector(s, ora[2])
+    assert relerr(g.get_array("DELY"), s.dely) <= 1e-6
+    S.check_convergence(g)
+    lo.check_convergence(s)
+    assert abs(g.DIMACS_error - s.DIMACS_error) <= 1e-6 * max(1.0, s.DIMACS_error)
+    g.close()
+
+
+def test_schur_matrix_parity_1e11(pkg, golden_dir):
+    """north_star: assembled Schur matrix within 1e-11 relative Frobenius error for the SAME W (general + LP + rank-one)."""
+    from oracle import loraine_oracle as lo
+    from loraine_jl_b200 import solver as S
+    for name, opts in (("theta1", OPTS_SDPA), ("control1", OPTS_SDPA), ("tru3", OPTS_SDPA),
+                       ("control1", dict(OPTS_SDPA, schur_split=1, datasparsity=8))):
+        z, arrays = golden(golden_dir, name)
+        opt, ora = make_pair(pkg, arrays, opts)
+        g, s = step_both(pkg, opt, ora, 2)
+        S.find_mu(g); S.prepare_W(g)
+        g._call("lrn_residuals"); g._call("lrn_schur_assemble")
+        H = g.get_array("H")
+        Wg = [g.get_array("W", i) for i in range(s.model.nlmi)]
+        Ho = lo.makeBBBBs(s.model, Wg)
+        if s.model.nlin > 0:
+            y, X, xl = S.get_solution(g)
+            sl = np.zeros(s.model.nlin)
+            import ctypes as C
+            g._call("lrn_get_slack", None, sl.ctypes.data_as(C.POINTER(C.c_double)))
+            Ho = Ho + lo.lp_schur(s.model, xl / sl)
+        assert relerr(H, Ho) <= 1e-11, name
+        g.close()
+    # rank-one path against the oracle's makeBBBB_rank1 with the device's G
+    arrays = pkg.problems.maxcut_torus(8, 12, 96)
+    o = dict(OPTS_SDPA, datarank=-1)
+    opt, ora = make_pair(pkg, arrays, o)
+    g, s = step_both(pkg, opt, ora, 2)
+    S.find_mu(g); S.prepare_W(g)
+    g._call("lrn_residuals"); g._call("lrn_schur_assemble")
+    H = g.get_array("H")
+    Ho = lo.makeBBBB_rank1(s.model.n, 1, s.model.B, [g.get_array("G", 0)])
+    assert relerr(H, Ho) <= 1e-11
+    # ... and the rank-one path equals the general path
+    opt2, ora2 = make_pair(pkg, arrays, dict(OPTS_SDPA, datarank=0))
+    g2, s2 = step_both(pkg, opt2, ora2, 2)
+    S.find_mu(g2); S.prepare_W(g2)
+    g2._call("lrn_residuals"); g2._call("lrn_schur_assemble")
+    assert relerr(g2.get_array("H"), H) <= 1e-10
+    g.close(); g2.close()
+
+
+@pytest.mark.parametrize("name", ["theta1", "control1", "tru3", "vib3"])
+def test_end_to_end_sdplib(pkg, golden_dir, name):
+    """objective within eDIMACS of the oracle / golden fixture, IP iteration count within +-1"""
+    z, arrays = golden(golden_dir, name)
+    opt = pkg.Optimizer()
+    for k, v in OPTS_SDPA.items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    opt.optimize()
+    s = opt.solver
+    assert s.status == 1
+    assert abs(s.iter - int(z["oracle_iters"])) <= 1
+    assert abs(s.primal_obj - float(z["oracle_obj"])) <= 1e-6 * (1 + abs(float(z["oracle_obj"])))
+    assert abs(s.dual_obj - float(z["oracle_dual_obj"])) <= 1e-5 * (1 + abs(float(z["oracle_obj"])))
+    if name == "theta1":
+        assert abs(opt.objective_value() - 23) <= 23e-6                    # examples/solve_sdpa.jl:61
+    s.close()
+
+
+def test_reference_jump_examples(pkg):
+    """the reference's own end-to-end assertions (examples/*.jl) through the CUDA path"""
+    for sense, want in (("Max", 0.8719210472), ("Min", -0.9779977649)):
+        spec = je.ex_corr(sense)
+        opt = pkg.Optimizer(); opt.set_attribute("verb", 0)
+        opt.copy_to(pkg.RawProblem(**je.fields(spec)), max_sense=spec["max_sense"])
+        opt.optimize()
+        assert opt.termination_status() == "OPTIMAL"
+        assert abs(opt.objective_value() - want) <= 1e-6 * abs(want)
+        opt.solver.close()
+    spec = je.ex_dist()
+    opt = pkg.Optimizer(); opt.set_attribute("verb", 0)
+    opt.copy_to(pkg.RawProblem(**je.fields(spec)), max_sense=False)
+    opt.optimize()
+    assert opt.termination_status() == "OPTIMAL" and abs(opt.objective_value() - 4 / 3) <= 1e-4
+    opt.solver.close()
+    spec = je.ex_maxcut4()
+    opt = pkg.Optimizer(); opt.set_attribute("verb", 0)
+    opt.copy_to(pkg.RawProblem(**je.fields(spec)), max_sense=True)
+    opt.optimize()
+    assert abs(opt.objective_value() - 17) <= 17e-5
+    opt.solver.close()
+    spec = je.ex_k_lp()                                                     # pure LP block, nlmi = 0
+    opt = pkg.Optimizer(); opt.set_attribute("verb", 0)
+    opt.copy_to(pkg.RawProblem(**je.fields(spec)), max_sense=True)
+    opt.optimize()
+    assert abs(opt.objective_value() - 4) <= 4e-6 and abs(opt.solver.y[0] - 2) <= 2e-6
+    opt.solver.close()
+
+
+@pytest.mark.parametrize("cfg", ["C2-mini", "C4-mini", "C5-mini"])
+def test_synthetic_minis_direct(pkg, cfg):
+    from oracle import loraine_oracle as lo, sdpa_io
+    c = pkg.problems.CONFIGS[cfg]
+    arrays = c["gen"]()
+    o = dict(c["options"], verb=0)
+    ref = lo.solve_raw(sdpa_io.raw_from_sdpa_arrays(*arrays), o)
+    opt = pkg.Optimizer()
+    for k, v in o.items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    opt.optimize()
+    s = opt.solver
+    assert s.status == ref.status == 1
+    assert abs(s.iter - ref.iter) <= 1
+    assert abs(s.primal_obj - ref.primal_obj) <= 1e-6 * (1 + abs(ref.primal_obj))
+    np.testing.assert_allclose(s.y, ref.y, atol=1e-4 * (1 + np.abs(ref.y).max()))
+    s.close()
+
+
+@pytest.mark.parametrize("prec", [0, 1, 2, 4])
+def test_cg_path_theta(pkg, golden_dir, prec):
+    """kit = 1: objective and CG / IP iteration counts against the oracle (parity unpinned by the reference)."""
+    from oracle import loraine_oracle as lo, sdpa_io
+    arrays = pkg.problems.theta_torus(6, 8)
+    o = dict(pkg.problems.CONFIGS["C3-mini"]["options"], verb=0, preconditioner=prec)
+    ref = lo.solve_raw(sdpa_io.raw_from_sdpa_arrays(*arrays), o)
+    opt = pkg.Optimizer()
+    for k, v in o.items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    opt.optimize()
+    s = opt.solver
+    assert s.status == 1
+    assert abs(s.primal_obj - 24.0) <= 1e-3                                # theta of the 6 x 8 torus is 24
+    assert abs(s.primal_obj - ref.primal_obj) <= 1e-4 * (1 + abs(ref.primal_obj))
+    assert abs(s.iter - ref.iter) <= 1
+    assert abs(s.cg_iter_tot - ref.cg_iter_tot) <= max(10, 0.15 * ref.cg_iter_tot)
+    s.close()
+
+
+def test_cg_operator_and_preconditioner_apply(pkg):
+    """MyA and MyM applied to a random vector vs the oracle's functors on the same iterate (LP block included)."""
+    from oracle import loraine_oracle as lo
+    from loraine_jl_b200 import solver as S
+    import ctypes as C
+    arrays = pkg.problems.multiblock_lp(3, 12, 10, 7)
+    o = dict(kit=1, preconditioner=1, erank=1, aamat=2, initpoint=1, verb=0, eDIMACS=1e-6)
+    opt, ora = make_pair(pkg, arrays, o)
+    g, s = step_both(pkg, opt, ora, 2)
+    for mod, st in ((S, g), (lo, s)):
+        st.iter += 1; st.cg_iter_pre = st.cg_iter_cor = 0
+        mod.find_mu(st); mod.prepare_W(st)
+    g._call("lrn_residuals"); g._call("lrn_rhs_predictor"); g._call("lrn_prec_prepare", 1)
+    ha = ora[2]
+    lo.Prec_for_CG_tilS_prep(s, ha)
+    x = np.random.default_rng(1).standard_normal(s.model.n)
+    out = np.zeros_like(x)
+    dpx = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    g._call("lrn_apply_operator", -1, dpx(x), dpx(out))
+    assert relerr(out, lo.MyA(s)(x)) <= 1e-8
+    g._call("lrn_apply_operator", 1, dpx(x), dpx(out))
+    assert relerr(out, lo.MyM(s, ha)(x)) <= 1e-6
+    g.close()

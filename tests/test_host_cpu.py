@@ -1,0 +1,117 @@
+"""CPU tests of the host side: C-ABI library loads and exports every symbol the headers declare (no compute calls
+without a GPU), SDPA reader / model preparation, option handling and clean errors."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import jump_examples as je
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrn_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from loraine_jl_b200 import _lib
+    L = C.CDLL(_lib.LIB_PATH)
+    names = _declared("loraine_b200.h") + _declared("loraine_b200_debug.h")
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(_lib.DECLARED_SYMBOLS) <= set(names)
+
+
+def test_create_without_gpu_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    n, bs, c, body = pkg.problems.theta_torus(4, 6)
+    opt = pkg.Optimizer()
+    opt.set_attribute("verb", 0)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(n, bs, c, body))
+    with pytest.raises(Exception) as ei:
+        opt.optimize()
+    assert "no CPU fallback" in str(ei.value) or "no usable" in str(ei.value)
+
+
+def test_non_float64_is_rejected(pkg):
+    """north_star: Optimizer{Float64xN} errors cleanly instead of falling back (examples/k.jl:8 uses Float64x2)."""
+    with pytest.raises(TypeError):
+        pkg.Optimizer(T=np.float32)
+    with pytest.raises(TypeError):
+        pkg.Optimizer(T="Float64x2")
+    md = pkg.prepare_model(pkg.RawProblem(**je.fields(je.ex_k_lp())))
+    with pytest.raises(TypeError):
+        pkg.load(md, dict(verb=0), T=np.longdouble)
+
+
+def test_options_surface(pkg):
+    """RawOptimizerAttribute keys = DEFAULT_OPTIONS (src/Solvers.jl:169-185, src/MOI_wrapper.jl:86-103)."""
+    want = {"kit": 0, "tol_cg": 1e-2, "tol_cg_up": 0.5, "tol_cg_min": 1e-7, "eDIMACS": 1e-7, "preconditioner": 1, "erank": 1,
+            "aamat": 1, "fig_ev": 0, "verb": 1, "datarank": 0, "initpoint": 0, "timing": 1, "maxit": 100, "datasparsity": 8}
+    assert pkg.DEFAULT_OPTIONS == want
+    opt = pkg.Optimizer()
+    with pytest.raises(KeyError):
+        opt.set_attribute("no_such_option", 1)
+    opt.set_attribute("kit", 1)
+    assert opt.get_attribute("kit") == 1
+
+
+def test_load_parameter_checks(pkg, capsys):
+    """src/Solvers.jl:263-291"""
+    md = pkg.prepare_model(pkg.RawProblem(**je.fields(je.ex_corr("Max"))))
+    s, _ = pkg.load(md, dict(verb=0, kit=7, erank=-2, datarank=-5, initpoint=3))
+    assert (s.kit, s.erank, s.datarank, s.initpoint) == (0, 1, 0, 1)
+    s, _ = pkg.load(md, dict(verb=0, kit=1, tol_cg=1e-9, tol_cg_min=1e-3, eDIMACS=1e-5, preconditioner=9))
+    assert s.tol_cg == 1e-3 and s.tol_cg_min == 1e-5 and s.preconditioner == 1
+
+
+def test_sdpa_roundtrip_and_model(pkg, tmp_path, golden_dir):
+    z = np.load(os.path.join(golden_dir, "vib3.npz"))
+    n, bs, c, body = int(z["n"]), [int(b) for b in z["bs"]], z["c"], z["body"]
+    f = tmp_path / "p.dat-s"
+    pkg.model.write_sdpa(str(f), n, bs, c, body)
+    n2, bs2, c2, body2 = pkg.read_sdpa(str(f))
+    assert n2 == n and bs2 == bs
+    np.testing.assert_array_equal(c2, c)
+    np.testing.assert_array_equal(body2, body)
+    raw = pkg.raw_from_sdpa_arrays(n, bs, c, body)
+    md = pkg.prepare_model(raw)
+    assert md.nlmi == sum(1 for b in bs if b > 0) and md.nlin == -sum(b for b in bs if b < 0)
+    for i, m in enumerate(md.msizes):
+        assert md.AA[i].shape == (n, m * m)
+        # both triangles stored: AA row k reshaped is symmetric
+        k = int(np.argmax(md.nzA[:, i]))
+        M = md.AA[i][k].toarray().reshape(m, m, order="F")
+        np.testing.assert_array_equal(M, M.T)
+    assert (np.diff(md.nzA[md.sigmaA[:, 0], 0]) <= 0).all()       # nnz-descending order
+
+
+def test_rank_one_factors(pkg):
+    n, bs, c, body = pkg.problems.theta_torus(3, 4)
+    md = pkg.prepare_model(pkg.raw_from_sdpa_arrays(n, bs, c, body), datarank=-1)
+    m = md.msizes[0]
+    for k in (0, m - 1, m, n - 1):
+        bk = md.B[0][k].toarray().ravel()
+        Ak = -md.AA[0][k].toarray().reshape(m, m, order="F")
+        np.testing.assert_allclose(np.outer(bk, bk), Ak, atol=1e-12)
+    n, bs, c, body = pkg.problems.large_schur(12, 30, 1)
+    with pytest.raises(ValueError):
+        pkg.prepare_model(pkg.raw_from_sdpa_arrays(n, bs, c, body), datarank=-1)
+
+
+def test_generators_shapes(pkg):
+    n, bs, c, body = pkg.problems.maxcut_torus(6, 8, 1)
+    assert n == 48 and bs == [48] and (body[body[:, 0] > 0][:, 2] == body[body[:, 0] > 0][:, 3]).all()
+    n, bs, c, body = pkg.problems.multiblock_lp(3, 10, 7, 5)
+    assert n == 30 and bs == [10, 10, 10, -7]
+    n, bs, c, body = pkg.problems.large_schur(20, 60, 3)
+    cnt = np.bincount(body[body[:, 0] > 0][:, 0].astype(int))[1:]
+    assert n == 60 and (cnt >= 1).all() and cnt.max() <= 15

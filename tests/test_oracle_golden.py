@@ -1,0 +1,126 @@
+"""CPU tests: the oracle (oracle/loraine_oracle.py) against every end-to-end known answer the reference's own tests hold
+for this path and against the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import loraine_oracle as lo
+from oracle import sdpa_io
+import jump_examples as je
+
+OPTS_SDPA = dict(kit=0, tol_cg=1e-2, tol_cg_min=1e-6, eDIMACS=1e-6, preconditioner=1, erank=1, aamat=2, verb=0, datarank=0,
+                 initpoint=1, maxit=100, datasparsity=8)           # examples/solve_sdpa.jl:43-54
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+    return z, sdpa_io.raw_from_sdpa_arrays(int(z["n"]), [int(b) for b in z["bs"]], z["c"], z["body"])
+
+
+def test_theta1_objective_23(golden_dir):
+    """examples/solve_sdpa.jl:61  @test objective_value(model) ~ 23 rtol = 1e-6"""
+    z, raw = _load(golden_dir, "theta1")
+    s = lo.solve_raw(raw, OPTS_SDPA)
+    assert s.status == 1
+    assert abs(s.primal_obj - 23.0) <= 1e-6 * 23.0
+    assert s.iter == int(z["oracle_iters"])
+    np.testing.assert_allclose([t["obj"] for t in s.trace], z["oracle_obj_trace"], rtol=1e-7)
+
+
+@pytest.mark.parametrize("name,optimum,rtol", [("control1", 17.78463, 2e-6), ("tru3", None, None), ("vib3", None, None)])
+def test_sdplib_fixtures(golden_dir, name, optimum, rtol):
+    z, raw = _load(golden_dir, name)
+    s = lo.solve_raw(raw, OPTS_SDPA)
+    assert s.status == 1
+    assert s.iter == int(z["oracle_iters"])
+    assert abs(s.primal_obj - float(z["oracle_obj"])) <= 1e-8 * (1 + abs(s.primal_obj))
+    if optimum is not None:
+        assert abs(s.primal_obj - optimum) <= rtol * optimum       # SDPLIB optimum
+    assert abs(s.primal_obj - s.dual_obj) <= 1e-5 * (1 + abs(s.primal_obj))
+
+
+def test_theta1_cg_variants(golden_dir):
+    """kit = 1 is not covered by any reference test: all preconditioners must reach the kit = 0 optimum."""
+    z, raw = _load(golden_dir, "theta1")
+    for prec in (0, 1, 2, 4):
+        o = dict(OPTS_SDPA, kit=1, preconditioner=prec)
+        s = lo.solve_raw(raw, o)
+        assert s.status == 1 and abs(s.primal_obj - 23.0) <= 1e-5 * 23.0, prec
+
+
+def test_ex_corr():
+    """examples/ex_corr.jl:30-31"""
+    for sense, want in (("Max", 0.8719210472), ("Min", -0.9779977649)):
+        spec = je.ex_corr(sense)
+        s = lo.solve_raw(sdpa_io.RawProblem(**je.fields(spec)), dict(kit=0, verb=0))
+        assert s.status == 1
+        assert abs(je.objective_value(spec, s.y) - want) <= 1e-6 * abs(want)
+
+
+def test_ex_dist():
+    """examples/ex_dist.jl:27-40"""
+    spec = je.ex_dist()
+    s = lo.solve_raw(sdpa_io.RawProblem(**je.fields(spec)), dict(kit=0, verb=0))
+    assert s.status == 1
+    assert abs(je.objective_value(spec, s.y) - 4 / 3) <= 1e-4
+    Q = np.zeros((4, 4))
+    for j in range(4):
+        for i in range(j + 1):
+            Q[i, j] = Q[j, i] = s.y[1 + je._tri(i, j)]
+    want = np.array([[0, 0, 0, 0], [0, 4, -2, -2], [0, -2, 4, -2], [0, -2, -2, 4]]) / 3
+    assert np.linalg.norm(Q - want) <= 1e-5 * np.linalg.norm(want)
+
+
+def test_ex_maxcut():
+    """examples/ex_maxcut.jl:43-47: the optimal partition {1,4} / {2,3} cuts every edge (weight 17)."""
+    spec = je.ex_maxcut4()
+    s = lo.solve_raw(sdpa_io.RawProblem(**je.fields(spec)), dict(kit=0, verb=0))
+    assert s.status == 1
+    assert abs(je.objective_value(spec, s.y) - 17.0) <= 1e-5 * 17
+    X = np.zeros((4, 4))
+    for j in range(4):
+        for i in range(j + 1):
+            X[i, j] = X[j, i] = s.y[je._tri(i, j)]
+    x = np.array([1, -1, -1, 1.0])
+    assert np.linalg.norm(X - np.outer(x, x)) <= 1e-4
+
+
+def test_k_lp():
+    """examples/k.jl:29-38 (Float64): objective 4, x = 2, shadow prices 0 and 2."""
+    spec = je.ex_k_lp()
+    s = lo.solve_raw(sdpa_io.RawProblem(**je.fields(spec)), dict(kit=0, verb=0))
+    assert s.status == 1
+    assert abs(je.objective_value(spec, s.y) - 4) <= 4e-6
+    assert abs(s.y[0] - 2) <= 2e-6
+    assert abs(s.X_lin[0]) <= 1e-6 and abs(s.X_lin[1] - 2) <= 2e-6
+
+
+def test_schur_aswritten_vs_vectorised(golden_dir):
+    """the literal F1/F3 loops of src/makeBBBB.jl:67-218 and the vectorised oracle path give the same H"""
+    rng = np.random.default_rng(0)
+    for name in ("theta1", "control1"):
+        z, raw = _load(golden_dir, name)
+        md = lo.prepare_model(raw, 0, 8)
+        W = []
+        for m in md.msizes:
+            N = rng.standard_normal((m, m))
+            W.append(N @ N.T / m + np.eye(m))
+        H1 = lo.makeBBBBs(md, W, aswritten=True)
+        H1 = np.tril(H1) + np.tril(H1, -1).T
+        H2 = lo.makeBBBBs(md, W)
+        assert np.linalg.norm(H1 - H2) <= 1e-13 * np.linalg.norm(H2)
+
+
+def test_golden_intermediates(golden_dir):
+    """H, W, dely of the third IP iteration of theta1 are reproduced bit-for-bit-ish by the oracle (regression pin)."""
+    z, raw = _load(golden_dir, "theta1")
+    got = {}
+    md = lo.prepare_model(raw, 0, 8)
+    s, ha = lo.load(md, OPTS_SDPA)
+    s.hooks["H"] = lambda s_, H: got.__setitem__(("H", s_.iter), H.copy())
+    s.hooks["W"] = lambda s_: got.__setitem__(("W", s_.iter), s_.W[0].copy())
+    s.hooks["dely_pred"] = lambda s_, h, d: got.__setitem__(("d", s_.iter), d.copy())
+    lo.solve(s, ha, max_iters=3)
+    for key, arr in (("H", z["H3"]), ("W", z["W3"]), ("d", z["dely3"])):
+        assert np.linalg.norm(got[(key, 3)] - arr) <= 1e-9 * np.linalg.norm(arr), key
