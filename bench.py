@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the Loraine.jl per-iteration interior-point hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C3|C4|C5|...-mini]
+
+A "step" is ONE interior-point iteration (find_mu, prepare_W, predictor, sigma_update, corrector, check_convergence) of
+the workload BASELINE.json's metric is quoted on: configs[1], the synthetic Max-Cut SDP n = 5000 with the rank-one Schur
+path (datarank = -1, kit = 0).  `value` = seconds per IP iteration with the problem and the iterate resident in HBM;
+`e2e` = the same iteration driven through the C ABI with the iterate in HOST memory (upload X, S, y / download y, X, S
+inside the timed region).  Multi-GPU (--gpus N under torchrun): this workload has a single PSD block, the path does not
+shard ("replicas only"): every rank runs an independent replica and `value` is job seconds per iteration.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sec/IP-iteration"
+UNIT = "s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--cpu-sample-n", type=int, default=2000, help="side of the reduced instance timed on the host CPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([t.strip() for t in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) >= 7 and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def algorithmic_flops(n_var, m, nnzB):
+    """rank-one assembly n_var^2 m (lower SYRK, 2 flop/MAC) + 2 nnz(B) m + n_var^2/2 ; Cholesky n_var^3/3"""
+    return dict(assemble=float(n_var) ** 2 * m + 2.0 * nnzB * m + 0.5 * float(n_var) ** 2, factor=float(n_var) ** 3 / 3.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores.  Julia is not installed in this image, so the
+    arm executes the NumPy/LAPACK oracle (oracle/loraine_oracle.py, kind = "port") with all host threads."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from oracle import loraine_oracle as lo, sdpa_io
+    cfg = pkg.problems.CONFIGS[args.workload]
+    full = cfg["gen"]
+    ns = args.cpu_sample_n
+    sample_note = ""
+    scale = 1.0
+    if args.workload == "C2":
+        rows = 25
+        cols = max(4, ns // rows)
+        arrays = pkg.problems.maxcut_torus(rows, cols, 5000)
+        nfull = 5000
+        scale = (nfull / float(rows * cols)) ** 3
+        sample_note = (f"max-cut torus {rows}x{cols} (n = m = {rows * cols}) from the same generator/seed; every phase of the "
+                       f"iteration is O(n^3) dense work, seconds scaled by (5000/{rows * cols})^3 = {scale:.1f} to the full size "
+                       f"(explicit extrapolation; the full-size CPU iteration takes minutes)")
+    else:
+        arrays = full()
+        sample_note = "full-size instance"
+    o = dict(cfg["options"], verb=0)
+    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=int(o.get("datarank", 0)), kappa=int(o.get("datasparsity", 8)))
+    s, ha = lo.load(md, o)
+    lo.setup_solver(s, ha)
+    lo.initial_point(s)
+
+    def step():
+        lo.myIPstep(s, ha)
+        s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
+        lo.check_convergence(s)
+        if s.status != 0:
+            lo.initial_point(s)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    raw = (time.perf_counter() - t0) / args.steps
+    cores = os.cpu_count()
+    val = raw * scale
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=val * 1e3,
+                higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=workload_name(args.workload), sample=sample_note),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample_note, measured_s_per_iteration_on_sample=raw),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def workload_name(w):
+    return {"C2": "configs[1]: synthetic Max-Cut SDP (ex_maxcut.jl / maxG11 layout) n=5000, 1 PSD block m=5000, datarank=-1 rank-one "
+                  "Schur path, kit=0 (torus 50x100, +-1 weights, seed 5000)"}.get(w, w)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from loraine_jl_b200 import solver as S, _lib
+    L = _lib.lib()
+    L.lrn_dbg_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    L.lrn_dbg_gemm_profile.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+
+    cfg = pkg.problems.CONFIGS[args.workload]
+    arrays = cfg["gen"]()
+    opt = pkg.Optimizer()
+    for k, v in dict(cfg["options"], verb=0, device=local).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    s, ha = opt.solver, opt.halpha
+    S.setup_solver(s, ha)
+    S.initial_point(s)
+    md = s.model
+
+    def step():
+        S.myIPstep(s, ha)
+        s.itertime = 0.0
+        s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
+        S.check_convergence(s)
+        if s.status != 0:               # converged (or failed): restart the same solve so that every step is a real iteration
+            S.initial_point(s)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- timed region: device-resident iterations -------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s.timers(reset=True)
+    launches0 = L.lrn_kernel_launches()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    t_dev = time.perf_counter() - t0
+    launches = L.lrn_kernel_launches() - launches0
+    phase = s.timers(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- e2e: the iterate lives in HOST memory; upload before / download after every iteration ------------------------
+    y, X, xl = S.get_solution(s)
+    PD = C.POINTER(C.c_double)
+    Sm = [np.zeros((m, m), order="F") for m in md.msizes]
+    sl = np.zeros(md.nlin)
+    Sp = (PD * max(1, md.nlmi))(*[x.ctypes.data_as(PD) for x in Sm])
+    s._call("lrn_get_slack", Sp, sl.ctypes.data_as(PD) if md.nlin else None)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    Xh = [np.asfortranarray(pin(x.T).T) for x in X]
+    Sh = [np.asfortranarray(pin(x.T).T) for x in Sm]
+    yh, xlh, slh = pin(y), pin(xl), pin(sl)
+    h2d = sum(x.nbytes for x in Xh) + sum(x.nbytes for x in Sh) + yh.nbytes + xlh.nbytes + slh.nbytes
+    d2h = h2d
+    e2e_steps = max(2, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        S.set_iterate(s, Xh, Sh, yh, xlh, slh)
+        S.myIPstep(s, ha)
+        s.itertime = 0.0
+        S.check_convergence(s)
+        yy, XX, xx = S.get_solution(s)
+        s._call("lrn_get_slack", Sp, sl.ctypes.data_as(PD) if md.nlin else None)
+        for a, b_ in zip(Xh, XX):
+            a[...] = b_
+        for a, b_ in zip(Sh, Sm):
+            a[...] = b_
+        yh[...] = yy
+        if md.nlin:
+            xlh[...] = xx
+            slh[...] = sl
+        if s.status != 0:
+            s.status = 0
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    # ---- roofline pass: per-launch CUDA events around the dominant kernel (the DMMA GEMM) ---------------------------
+    ms, fl, nl = C.c_double(), C.c_double(), C.c_int64()
+    L.lrn_dbg_gemm_profile(1, None, None, None)
+    prof_steps = 1
+    for _ in range(prof_steps):
+        step()
+    L.lrn_dbg_gemm_profile(0, C.byref(ms), C.byref(fl), C.byref(nl))
+    peak = C.c_double()
+    L.lrn_dbg_peak(0, C.byref(peak))
+
+    tmax = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(tmax[0]), float(tmax[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sec_per_iter = t_dev / (args.steps * world)
+    e2e_val = t_e2e / (e2e_steps * world)
+    nnzB = md.B[0].nnz if md.B else 0
+    alg = algorithmic_flops(md.n, md.msizes[0] if md.nlmi else 0, nnzB)
+    asm_ms = phase["schur_assemble"][0] / max(1, phase["schur_assemble"][1])
+    fac_ms = phase["schur_factor"][0] / max(1, phase["schur_factor"][1])
+    achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+    line = dict(
+        metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=1e3 * t_dev / args.steps, higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload=workload_name(args.workload), n_var=md.n, msizes=md.msizes[:4], nlin=md.nlin,
+                    options=cfg["options"], l2="inputs larger than L2 (every dense operand is 200 MB; 21 resident m x m matrices)",
+                    parallelism="replicas only" if world > 1 else "single GPU"),
+        e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=e2e_steps),
+        gpu_launches=int(launches),
+        clocks=clocks,
+        phases_ms_per_iteration={k: v[0] / args.steps for k, v in phase.items()},
+        schur=dict(assemble_ms=asm_ms, assemble_tflops=alg["assemble"] / (asm_ms * 1e-3) / 1e12 if asm_ms > 0 else None,
+                   factor_ms=fac_ms, factor_tflops=alg["factor"] / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else None,
+                   assemble_plus_factor_tflops=(alg["assemble"] + alg["factor"]) / ((asm_ms + fac_ms) * 1e-3) / 1e12
+                   if asm_ms + fac_ms > 0 else None),
+        roofline=dict(bound="tensor", kernel="dgemm_dmma_kernel (FP64 DMMA GEMM: SVD panel products, congruences, SYRK, TRSM)",
+                      achieved=achieved, peak=peak.value, unit="TFLOP/s", frac=achieved / peak.value if peak.value else None,
+                      traffic=None, launches_profiled=int(nl.value), kernel_ms_per_step=ms.value / prof_steps,
+                      peak_source="measured in this run: register-resident mma.sync.m8n8k4.f64 loop on all SMs "
+                                  "(MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.4 TFLOP/s)"),
+        stats=s.stats(),
+    )
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(pkg, args)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(pkg, args):
+    """oracle (kind "port") timed on this box's host cores on a bounded sample of the same workload"""
+    from oracle import loraine_oracle as lo, sdpa_io
+    cfg = pkg.problems.CONFIGS[args.workload]
+    scale, note = 1.0, "full-size instance"
+    if args.workload == "C2":
+        rows, cols = 25, max(4, args.cpu_sample_n // 25)
+        arrays = pkg.problems.maxcut_torus(rows, cols, 5000)
+        scale = (5000.0 / (rows * cols)) ** 3
+        note = (f"1 IP iteration (after 1 warm-up iteration) of the same generator at torus {rows}x{cols} (n = m = {rows * cols}); all phases are "
+                f"O(n^3): seconds scaled by (5000/{rows * cols})^3 = {scale:.0f} to the full size (explicit extrapolation)")
+    else:
+        arrays = cfg["gen"]()
+    o = dict(cfg["options"], verb=0)
+    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=int(o.get("datarank", 0)), kappa=int(o.get("datasparsity", 8)))
+    s, ha = lo.load(md, o)
+    lo.setup_solver(s, ha)
+    lo.initial_point(s)
+    lo.myIPstep(s, ha)
+    lo.check_convergence(s)
+    t0 = time.perf_counter()
+    lo.myIPstep(s, ha)
+    lo.check_convergence(s)
+    raw = time.perf_counter() - t0
+    return dict(value=raw * scale, unit=UNIT, cores=os.cpu_count(), kind="port", sample=note, measured_s_per_iteration_on_sample=raw)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -26,6 +26,10 @@ int32_t lrn_dbg_lanczos(int32_t m, const double* T, int32_t nev_top, double tol,
 /* device micro-benchmarks: kind 0 = DMMA (mma.sync m8n8k4 f64) register-resident peak, 1 = DFMA peak, 2 = HBM copy GB/s */
 int32_t lrn_dbg_peak(int32_t kind, double* value);
 
+/* per-launch timing of the DMMA GEMM kernel (roofline bookkeeping of bench.py): mode 1 starts recording one CUDA-event pair
+ * per launch on the launching stream, mode 0 stops and returns total kernel milliseconds, algorithmic flops and launches */
+int32_t lrn_dbg_gemm_profile(int32_t mode, double* ms, double* flops, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

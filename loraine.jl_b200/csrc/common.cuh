@@ -74,6 +74,8 @@ struct DevBuf {
         if (count == 0) return;
         LRN_CUDA(cudaMalloc(&p, count * sizeof(T)));
         LRN_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+        // the memset runs on the legacy stream, the library works on non-blocking streams: order them explicitly
+        LRN_CUDA(cudaDeviceSynchronize());
     }
     void release() {
         if (p) cudaFree(p);

@@ -209,6 +209,15 @@ int32_t lrn_dbg_lanczos(int32_t m, const double* T, int32_t nev_top, double tol,
     });
 }
 
+int32_t lrn_dbg_gemm_profile(int32_t mode, double* ms, double* flops, int64_t* launches) {
+    return guard([&]() -> int32_t {
+        long long n = 0;
+        gemm_profile(mode, ms, flops, &n);
+        if (launches) *launches = n;
+        return LRN_OK;
+    });
+}
+
 int32_t lrn_dbg_peak(int32_t kind, double* value) {
     return guard([&]() -> int32_t {
         cudaEvent_t e0, e1;

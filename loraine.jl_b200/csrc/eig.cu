@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
     const double abs_tol = P.relative ? 0.0 : 1.0e-18 * fro;
     const double rel_tol = 1.0e-15;
 
-    for (int sweep = 0; sweep < 40; sweep++) {
+    for (int sweep = 0; sweep < P.max_sweeps; sweep++) {
         if (tid == 0) rotated = 0;
         __syncthreads();
         for (int r = 0; r < n2 - 1; r++) {
@@ -327,6 +327,7 @@ void SvdWork::ensure(int m_) {
         pi[1] = 2;
     }
     slotmap.upload(pi);
+    inner_sweeps = (nblk == 2) ? 40 : 1;   // a single pair is diagonalised completely in one visit
     LRN_CUDA(cudaDeviceSynchronize());
 }
 
@@ -358,6 +359,9 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
             EigSmallParams e;
             e.A = w.gram.p; e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; e.n = 64;
             e.V = w.rot.p; e.ldv = 64; e.sV = 4096; e.relative = 1; e.offmax = w.offmax.p; e.batch = pairs;
+            e.max_sweeps = w.inner_sweeps;   // one cyclic sweep per visit converges in as many outer sweeps as full diagonalisation
+            // note: no sorting inside the pair rotations -- with the round-robin block ordering it makes columns migrate
+            // between blocks and the sweep no longer visits every column pair (observed: no convergence)
             jacobi_eig_small(e, st);
             GemmParams u;                       // rotate [A;V] panels and scatter them to next round's arrangement
             u.A = cur; u.B = w.rot.p; u.C = nxt;

@@ -29,6 +29,7 @@ struct EigSmallParams {
     double* offmax = nullptr;    // optional: atomicMax of max_{i<j} |a_ij|/sqrt(|a_ii a_jj|) of the INPUT matrices
     double* minval = nullptr;    // optional: per batch smallest eigenvalue (stride 1)
     int batch = 1;
+    int max_sweeps = 40;         // cyclic sweeps over all pairs (1 = a single sweep, used inside the block-Jacobi SVD)
 };
 void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st);
 
@@ -43,6 +44,7 @@ struct SvdWork {
     DevBuf<double> sv;           // mp singular values (unsorted)
     DevBuf<int> perm;            // mp
     int splits = 1, Kc = 0;
+    int inner_sweeps = 1;
     void ensure(int m_);
 };
 

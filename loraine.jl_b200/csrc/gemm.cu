@@ -197,6 +197,12 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
 }
 
 std::atomic<long long> g_launches{0};
+
+// optional per-launch profiling (bench roofline): CUDA events around every DMMA GEMM launch on its own stream
+struct ProfRec { cudaEvent_t a, b; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+constexpr size_t PROF_CAP = 60000;
 }  // namespace
 std::atomic<long long> g_kernel_launches{0};
 namespace {
@@ -211,8 +217,21 @@ void launch_cfg(const GemmParams& p, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * p.batch2));
+    const bool prof = g_prof_on && g_prof.size() < PROF_CAP;
+    ProfRec rec;
+    if (prof) {
+        LRN_CUDA(cudaEventCreate(&rec.a));
+        LRN_CUDA(cudaEventCreate(&rec.b));
+        double kk = (p.K_last > 0 && p.batch2 > 1) ? ((double)p.K * (p.batch2 - 1) + p.K_last) / p.batch2 : (double)p.K;
+        rec.flops = 2.0 * p.M * (double)p.N * kk * p.batch * p.batch2 * (p.lower ? 0.5 : 1.0);
+        LRN_CUDA(cudaEventRecord(rec.a, st));
+    }
     kern<<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(p);
     LRN_CHECK_LAUNCH();
+    if (prof) {
+        LRN_CUDA(cudaEventRecord(rec.b, st));
+        g_prof.push_back(rec);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
@@ -249,5 +268,26 @@ void gemm(const GemmParams& p, cudaStream_t stream) {
 }
 
 long long gemm_launch_count() { return g_launches.load(); }
+
+void gemm_profile(int mode, double* ms, double* flops, long long* launches) {
+    if (mode == 1) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        g_prof.clear();
+        g_prof_on = true;
+        return;
+    }
+    g_prof_on = false;
+    LRN_CUDA(cudaDeviceSynchronize());
+    double t = 0.0, f = 0.0;
+    for (auto& r : g_prof) {
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) { t += e; f += r.flops; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    if (ms) *ms = t;
+    if (flops) *flops = f;
+    if (launches) *launches = (long long)g_prof.size();
+    g_prof.clear();
+}
 
 }  // namespace lrn

@@ -52,5 +52,7 @@ inline void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const dou
 
 // Number of DMMA GEMM kernel launches issued so far by this process (bench `gpu_launches` bookkeeping).
 long long gemm_launch_count();
+// mode 1: start recording one CUDA-event pair per GEMM launch; mode 0: stop, synchronise and report the totals
+void gemm_profile(int mode, double* ms, double* flops, long long* launches);
 
 }  // namespace lrn

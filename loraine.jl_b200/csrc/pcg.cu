@@ -115,7 +115,7 @@ int block_tau(lrn_solver* h, Block& B, int k, std::vector<double>& top_vals) {
     const int m = B.m, ld = B.ld;
     if (!B.U.p()) { B.U.init(m, k); B.MU.init(m, k); B.ZY.init(m, k); B.Zf.init(m, m); }
     top_vals.assign(k, 0.0);
-    const double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-10;
+    const double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-8;
     LanczosResult r = lanczos_extreme(B.W.p(), m, ld, 3, k, top_vals.data(), B.U.p(), B.U.ld, tol, h->lan, st);
     h->stat_lanczos_iters += r.iters;
     if (!r.converged) h->stat_lanczos_fail++;

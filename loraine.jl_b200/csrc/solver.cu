@@ -250,7 +250,7 @@ void build_block(lrn_solver* h, Block& B) {
 // smallest eigenvalue of the symmetric m x m matrix T (device)
 double lambda_min(lrn_solver* h, const double* T, int m, int ld) {
     Phase ph(h, LRN_T_EIGMIN);
-    double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-10;
+    double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-8;
     LanczosResult r = lanczos_extreme(T, m, ld, 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st);
     h->stat_lanczos_iters += r.iters;
     if (!r.converged) h->stat_lanczos_fail++;
