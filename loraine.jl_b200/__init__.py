@@ -9,3 +9,4 @@ library cannot be loaded.
 from .model import MyModel, RawProblem, read_sdpa, raw_from_sdpa_arrays, prepare_model  # noqa: F401
 from .solver import (DEFAULT_OPTIONS, MySolver, Halpha, PosDefException, load, solve, Optimizer)  # noqa: F401
 from . import problems  # noqa: F401
+from . import dist  # noqa: F401

@@ -68,8 +68,8 @@ def lib():
         "lrn_kernel_launches": (i64, []),
         "lrn_stats": (i32, [vp, pi64]),
         "lrn_set_option": (i32, [vp, C.c_char_p, dbl]),
-        "lrn_dist_unique_id": (i32, [vp]),
-        "lrn_dist_init": (i32, [vp, i32, i32, vp]),
+        "lrn_dist_unique_id": (i32, [C.c_char_p]),
+        "lrn_dist_init": (i32, [vp, i32, i32, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

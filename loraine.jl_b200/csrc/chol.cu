@@ -9,60 +9,91 @@ namespace {
 
 constexpr int DB = CHOL_DB;
 constexpr int SLD = DB + 1;
+constexpr size_t POTRF_SMEM = (2 * DB * SLD + DB + 2 + 4 * DB) * sizeof(double);
 
+// One CTA factors a 64x64 diagonal block held in REGISTERS (each of the 256 threads owns a cyclic 4x4 sub-tile: rows
+// ti+16a, columns tj+16b), two barriers per column; the inverse of the factor is then built row by row in shared memory
+// (4 partial dot products per entry).  ~15 us instead of ~100 us for the previous shared-memory version.
 __global__ void __launch_bounds__(256)
     potrf_diag_kernel(double* __restrict__ A, int lda, int nb, double* __restrict__ dinv, int* __restrict__ info, int base) {
     extern __shared__ double sm[];
-    double* s = sm;                 // L      [DB][SLD]
-    double* x = sm + DB * SLD;      // L^{-1} [DB][SLD]
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < DB * DB; idx += 256) {
-        int i = idx % DB, j = idx / DB;
-        double v = 0.0;
-        if (i < nb && j < nb && i >= j) v = A[(size_t)j * lda + i];
-        if (i >= nb && i == j) v = 1.0;   // identity padding keeps the inverse well defined
-        s[i * SLD + j] = v;
-        x[i * SLD + j] = 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < nb; j++) {
-        if (tid == 0) {
-            double d = s[j * SLD + j];
-            if (!(d > 0.0)) {          // also catches NaN
-                if (*info == 0) *info = base + j + 1;
+    double* sL = sm;                      // factor (lower), later read by the inversion   [DB][SLD]
+    double* sX = sm + DB * SLD;           // inverse                                        [DB][SLD]
+    double* colbuf = sX + DB * SLD;       // [DB]
+    double* dbuf = colbuf + DB;           // [2]
+    double (*part)[DB] = reinterpret_cast<double (*)[DB]>(dbuf + 2);   // [4][DB]
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    double r[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int i = ti + 16 * a, k = tj + 16 * b;
+            double v = 0.0;
+            if (i < nb && k < nb) v = (i >= k) ? A[(size_t)k * lda + i] : A[(size_t)i * lda + k];   // symmetric fill from the lower part
+            else if (i == k) v = 1.0;                                                            // identity padding
+            r[a][b] = v;
+        }
+    for (int j = 0; j < DB; j++) {
+        const int ja = j >> 4, jm = j & 15;
+        if (ti == jm && tj == jm) {                       // owner of the diagonal entry
+            double d = 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; a++) if (a == ja) d = r[a][a];
+            if (!(d > 0.0)) {
+                if (j < nb && *info == 0) *info = base + j + 1;
                 d = 1.0;
             }
-            s[j * SLD + j] = sqrt(d);
+            dbuf[j & 1] = sqrt(d);
         }
         __syncthreads();
-        const double djj = s[j * SLD + j];
-        for (int i = j + 1 + tid; i < nb; i += 256) s[i * SLD + j] /= djj;
-        __syncthreads();
-        const int t = nb - 1 - j;
-        for (int idx = tid; idx < t * t; idx += 256) {
-            int ii = idx % t, kk = idx / t;
-            if (ii >= kk) {
-                int i = j + 1 + ii, k = j + 1 + kk;
-                s[i * SLD + k] -= s[i * SLD + j] * s[k * SLD + j];
+        const double djj = dbuf[j & 1];
+        if (tj == jm) {                                   // owners of column j publish l(:,j)
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int i = ti + 16 * a;
+                double v = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) if (b == ja) v = r[a][b];
+                v = (i > j) ? v / djj : (i == j ? djj : 0.0);
+                colbuf[i] = v;
+                sL[i * SLD + j] = v;
             }
         }
         __syncthreads();
-    }
-    // inverse of the lower-triangular factor, one thread per column
-    if (tid < DB) {
-        const int c = tid;
-        x[c * SLD + c] = 1.0 / s[c * SLD + c];
-        for (int i = c + 1; i < DB; i++) {
-            double acc = 0.0;
-            for (int k = c; k < i; k++) acc += s[i * SLD + k] * x[k * SLD + c];
-            x[i * SLD + c] = -acc / s[i * SLD + i];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int i = ti + 16 * a;
+            const double li = colbuf[i];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int k = tj + 16 * b;
+                if (i > j && k > j) r[a][b] -= li * colbuf[k];
+            }
         }
+        // colbuf of step j is re-written only after the next barrier pair; dbuf is double buffered
     }
     __syncthreads();
+    // inverse, row by row: x(i,c) = -( sum_{k=c}^{i-1} L(i,k) x(k,c) ) / L(i,i),  x(i,i) = 1 / L(i,i)
+    const int c = tid & 63, pr = tid >> 6;
+    for (int i = 0; i < DB; i++) {
+        double acc = 0.0;
+        for (int k = c + pr; k < i; k += 4) acc += sL[i * SLD + k] * sX[k * SLD + c];
+        part[pr][c] = acc;
+        __syncthreads();
+        if (pr == 0) {
+            double v = 0.0;
+            const double lii = sL[i * SLD + i];
+            if (c == i) v = 1.0 / lii;
+            else if (c < i) v = -(part[0][c] + part[1][c] + part[2][c] + part[3][c]) / lii;
+            sX[i * SLD + c] = v;
+        }
+        __syncthreads();
+    }
     for (int idx = tid; idx < DB * DB; idx += 256) {
         int i = idx % DB, j = idx / DB;
-        if (i < nb && j < nb && i >= j) A[(size_t)j * lda + i] = s[i * SLD + j];
-        dinv[(size_t)j * DB + i] = (i < nb && j < nb) ? x[i * SLD + j] : 0.0;
+        if (i < nb && j < nb && i >= j) A[(size_t)j * lda + i] = sL[i * SLD + j];
+        dinv[(size_t)j * DB + i] = (i < nb && j < nb) ? sX[i * SLD + j] : 0.0;
     }
 }
 
@@ -73,9 +104,21 @@ int pick_nb(int n) {
     return 64;
 }
 
+// P (rows x kb, below a factored kb x kb diagonal block Akk) <- P * inv(L_kk)^T, 64 columns at a time
+void panel_trsm(double* P, int rows, int kb, const double* Akk, const double* dk, int lda, cudaStream_t st) {
+    for (int j = 0; j < kb; j += DB) {
+        const int jb = (kb - j < DB) ? (kb - j) : DB;
+        double* Pj = P + (size_t)j * lda;
+        // Pj -= P[:,0:j] * L[k+j : k+j+jb, k : k+j]^T
+        if (j > 0) gemm_nt(st, rows, jb, j, -1.0, P, lda, Akk + j, lda, 1.0, Pj, lda);
+        // Pj <- Pj * inv(L_jj)^T   (in place: every CTA owns its rows and a single N tile)
+        gemm_nt(st, rows, jb, jb, 1.0, Pj, lda, dk + (size_t)(j / DB) * DB * DB, DB, 0.0, Pj, lda);
+    }
+}
+
 void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, cudaStream_t st) {
     if (n <= DB) {
-        potrf_diag_kernel<<<1, 256, 2 * DB * SLD * sizeof(double), st>>>(A, lda, n, dinv, info, base);
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(A, lda, n, dinv, info, base);
         LRN_CHECK_LAUNCH();
         return;
     }
@@ -88,16 +131,7 @@ void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, cuda
         const int rows = n - k - kb;
         if (rows <= 0) break;
         double* P = A + (size_t)k * lda + (k + kb);          // rows x kb panel below the diagonal block
-        for (int j = 0; j < kb; j += DB) {
-            const int jb = (kb - j < DB) ? (kb - j) : DB;
-            double* Pj = P + (size_t)j * lda;
-            if (j > 0) {
-                // Pj -= P[:,0:j] * L[k+j : k+j+jb, k : k+j]^T
-                gemm_nt(st, rows, jb, j, -1.0, P, lda, Akk + j, lda, 1.0, Pj, lda);
-            }
-            // Pj <- Pj * inv(L_jj)^T   (in place: every CTA owns its rows and a single N tile)
-            gemm_nt(st, rows, jb, jb, 1.0, Pj, lda, dk + (size_t)(j / DB) * DB * DB, DB, 0.0, Pj, lda);
-        }
+        panel_trsm(P, rows, kb, Akk, dk, lda, st);
         // trailing update, lower triangle only
         GemmParams p;
         p.A = P; p.B = P; p.C = A + (size_t)(k + kb) * lda + (k + kb);
@@ -163,12 +197,21 @@ __global__ void zero_upper_kernel(double* A, int n, int lda) {
 
 }  // namespace
 
+void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+        configured = true;
+    }
+    chol_rec(Apanel, w, lda, dinv, info, base, st);
+    if (rows > w) panel_trsm(Apanel + w, rows - w, w, Apanel, dinv, lda, st);
+}
+
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st) {
     work.ensure(n);
     static bool configured = false;
     if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(2 * DB * SLD * sizeof(double))));
+        LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
         configured = true;
     }
     LRN_CUDA(cudaMemsetAsync(work.info_ptr(), 0, sizeof(int), st));
@@ -197,6 +240,19 @@ void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x
             LRN_CHECK_LAUNCH();
         }
         LRN_CUDA(cudaMemcpyAsync(x, tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+}
+
+void trsm_left_lower_trans(const double* L, int n, int lda, const CholWork& work, double* Y, int ldy, int ncols, cudaStream_t st) {
+    if (n <= 0 || ncols <= 0) return;
+    const int nblk = (int)cdiv(n, DB);
+    for (int b = nblk - 1; b >= 0; b--) {
+        const int j0 = b * DB, jb = (n - j0 < DB) ? (n - j0) : DB;
+        double* Yj = Y + j0;
+        // X_j = inv(L_jj)^T Y_j   (in place: one M tile, every CTA reads exactly the columns it writes)
+        gemm_tn(st, jb, ncols, jb, 1.0, work.dinv.p + (size_t)b * DB * DB, DB, Yj, ldy, 0.0, Yj, ldy);
+        // Y[0:j0, :] -= L[j0:j0+jb, 0:j0]^T X_j
+        if (j0 > 0) gemm_tn(st, j0, ncols, jb, -1.0, L + j0, lda, Yj, ldy, 1.0, Y, ldy);
     }
 }
 

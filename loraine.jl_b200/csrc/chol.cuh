@@ -25,8 +25,16 @@ struct CholWork {
 // (inside diagonal 128-tiles it may be overwritten with don't-care values). Enqueues only; read `work.info` after a sync.
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st);
 
+// Factor one column panel: the w x w diagonal block at the top of `Apanel` (rows x w) and the TRSM of the rows below it.
+// `dinv` points at the 64x64 inverse blocks of this panel, `base` is the global index of its first column (for info).
+void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, cudaStream_t st);
+
 // x <- L^{-1} x (which=1), x <- L^{-T} x (which=2), both (which=3). `tmp` has n doubles. Uses work.dinv of the same factor.
 void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st);
+
+// Y <- L^{-T} Y for an n x ncols right-hand-side block (in place), blocked with the inverted diagonal blocks of `work`:
+// used for G = L_S^{-T} (U D^{1/2}) in the NT scaling (no accumulated right singular vectors needed).
+void trsm_left_lower_trans(const double* L, int n, int lda, const CholWork& work, double* Y, int ldy, int ncols, cudaStream_t st);
 
 // Zero the strict upper triangle (so the factor can be used as a dense GEMM operand).
 void zero_strict_upper(double* A, int n, int lda, cudaStream_t st);

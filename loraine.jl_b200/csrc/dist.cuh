@@ -25,6 +25,15 @@ struct DistCtx {
     int rank = 0, world = 1;
 };
 
+struct CholWork;
+// Distributed right-looking Cholesky, 1-D block-cyclic by column panels of width pw (panel p -> rank p % world).
+// On entry every rank holds its OWN panels of the lower triangle of A (other panels: don't care); on return every rank
+// holds the complete factor L and all inverse diagonal blocks (panels are broadcast with ncclBroadcast as they are
+// finished, the receivers store them), so triangular solves run replicated without further communication.
+void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int pw, DevBuf<double>& panelbuf, cudaStream_t st);
+// in-place sum of a device buffer over all ranks
+void dist_allreduce_sum(double* buf, size_t count, DistCtx& ctx, cudaStream_t st);
+
 #define LRN_NCCL(call)                                                                         \
     do {                                                                                       \
         ncclResult_t r__ = (call);                                                             \

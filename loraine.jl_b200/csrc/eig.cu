@@ -93,37 +93,39 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
                 cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
             }
             __syncthreads();
-            for (int item = tid; item < h * n2; item += 256) {     // rows p,q  <-  J^T A
-                int k = item / n2, j = item - k * n2;
-                double s = sn[k];
-                if (s != 0.0) {
-                    double c = cs[k];
-                    int p = pp[k], q = qq[k];
+            // every warp owns 4 of the (at most 32) disjoint pairs; lanes run along the row / column
+            for (int kk = 0; kk < 4; kk++) {                         // rows p,q  <-  J^T A
+                const int k = (tid >> 5) * 4 + kk;
+                if (k >= h) break;
+                const double s = sn[k];
+                if (s == 0.0) continue;
+                const double c = cs[k];
+                const int p = pp[k], q = qq[k];
+                for (int j = tid & 31; j < n2; j += 32) {
                     double ap = a[p * ELD + j], aq = a[q * ELD + j];
                     a[p * ELD + j] = c * ap - s * aq;
                     a[q * ELD + j] = s * ap + c * aq;
                 }
             }
             __syncthreads();
-            for (int item = tid; item < h * n2; item += 256) {     // cols p,q  <-  A J ;  V J
-                int k = item / n2, i = item - k * n2;
-                double s = sn[k];
-                if (s != 0.0) {
-                    double c = cs[k];
-                    int p = pp[k], q = qq[k];
+            for (int kk = 0; kk < 4; kk++) {                         // cols p,q  <-  A J ;  V J ; pivot entries zeroed
+                const int k = (tid >> 5) * 4 + kk;
+                if (k >= h) break;
+                const double s = sn[k];
+                if (s == 0.0) continue;
+                const double c = cs[k];
+                const int p = pp[k], q = qq[k];
+                for (int i = tid & 31; i < n2; i += 32) {
                     double ap = a[i * ELD + p], aq = a[i * ELD + q];
-                    a[i * ELD + p] = c * ap - s * aq;
-                    a[i * ELD + q] = s * ap + c * aq;
+                    double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
+                    if (i == p) nq_ = 0.0;
+                    if (i == q) np_ = 0.0;
+                    a[i * ELD + p] = np_;
+                    a[i * ELD + q] = nq_;
                     double vp = v[i * ELD + p], vq = v[i * ELD + q];
                     v[i * ELD + p] = c * vp - s * vq;
                     v[i * ELD + q] = s * vp + c * vq;
                 }
-            }
-            __syncthreads();
-            if (tid < h && sn[tid] != 0.0) {
-                int p = pp[tid], q = qq[tid];
-                a[p * ELD + q] = 0.0;
-                a[q * ELD + p] = 0.0;
             }
             __syncthreads();
         }
@@ -171,10 +173,10 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
 // ---------------------------------------------------------------------------------------------------------------
 // one-sided block Jacobi helpers
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void svd_init_kernel(const double* __restrict__ A, int lda, int m, int mp, double* __restrict__ W, int ldw) {
+__global__ void svd_init_kernel(const double* __restrict__ A, int lda, int m, int mp, int rows, double* __restrict__ W, int ldw) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;    // row in stacked buffer
     int j = blockIdx.y;                               // column
-    if (i >= m + mp) return;
+    if (i >= rows) return;
     double v;
     if (i < m) v = (j < m) ? A[(size_t)j * lda + i] : 0.0;
     else v = (i - m == j) ? 1.0 : 0.0;
@@ -212,7 +214,7 @@ __global__ void svd_gather_kernel(const double* __restrict__ W, int ldw, int m, 
     int src = perm[r];
     if (i < m) {
         UD[(size_t)r * ldu + i] = W[(size_t)src * ldw + i];
-        V[(size_t)r * ldv + i] = W[(size_t)src * ldw + m + i];
+        if (V) V[(size_t)r * ldv + i] = W[(size_t)src * ldw + m + i];
     }
     if (i == 0) sigma[r] = sv[src];
 }
@@ -295,16 +297,17 @@ void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st) {
     LRN_CHECK_LAUNCH();
 }
 
-void SvdWork::ensure(int m_) {
-    if (m_ == m && buf0.p) return;
+void SvdWork::ensure(int m_, bool want_V_) {
+    if (m_ == m && buf0.p && want_V_ == want_V) return;
     m = m_;
+    want_V = want_V_;
     mp = round_up(m, 64);
-    ldw = pad_ld(m + mp);
+    ldw = pad_ld(want_V ? m + mp : m);
     size_t elems = (size_t)ldw * mp;
     buf0.alloc(elems);
     buf1.alloc(elems);
     const int nblk = mp / 32, pairs = nblk / 2;
-    splits = (int)std::min<long long>(8, std::max<long long>(1, 148 / pairs));
+    splits = (int)std::min<long long>(16, std::max<long long>(1, cdiv(296, pairs)));   // >= 2 CTAs per SM in the Gram GEMM
     Kc = round_up((int)cdiv(m, splits), 16);
     if (Kc < 64) Kc = 64;
     splits = (int)cdiv(m, Kc);
@@ -333,14 +336,16 @@ void SvdWork::ensure(int m_) {
 
 int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, double* V, int ldv, double* sigma, SvdWork& w,
                      double tol, int max_sweeps, cudaStream_t st) {
-    w.ensure(m);
+    const bool want_V = (V != nullptr);
+    w.ensure(m, want_V);
     const int mp = w.mp, ldw = w.ldw, nblk = mp / 32, pairs = nblk / 2, rounds = nblk - 1;
-    const int rows = m + mp;
+    const int rows = want_V ? m + mp : m;
+    static const bool trace = getenv("LRN_SVD_TRACE") != nullptr;
     double* cur = w.buf0.p;
     double* nxt = w.buf1.p;
     {
         dim3 grid((unsigned)cdiv(rows, 256), (unsigned)mp);
-        svd_init_kernel<<<grid, 256, 0, st>>>(A, lda, m, mp, cur, ldw);
+        svd_init_kernel<<<grid, 256, 0, st>>>(A, lda, m, mp, rows, cur, ldw);
         LRN_CHECK_LAUNCH();
     }
     const int splits = w.splits, Kc = w.Kc;
@@ -375,6 +380,7 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
         double off = 0.0;
         LRN_CUDA(cudaMemcpyAsync(&off, w.offmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
         LRN_CUDA(cudaStreamSynchronize(st));
+        if (trace) fprintf(stderr, "[lrn svd] m=%d sweep %d offmax %.3e\n", m, sweep + 1, off);
         if (off <= tol) break;
     }
     // after a whole number of sweeps the arrangement is back to the identity; singular values = column norms

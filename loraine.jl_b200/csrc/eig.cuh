@@ -45,11 +45,13 @@ struct SvdWork {
     DevBuf<int> perm;            // mp
     int splits = 1, Kc = 0;
     int inner_sweeps = 1;
-    void ensure(int m_);
+    bool want_V = true;
+    void ensure(int m_, bool want_V_ = true);
 };
 
 // On return (asynchronous): `U_D` (m x m, ldu) holds A*V = U*diag(sigma) with columns sorted by sigma descending,
 // `V` (m x m, ldv) the right singular vectors in the same order, `sigma` (m) the singular values.
+// V may be null: the right singular vectors are then not accumulated (one third fewer flops).
 // Returns the number of sweeps used (host-synchronises once per sweep to read the convergence measure).
 int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, double* V, int ldv, double* sigma, SvdWork& w,
                      double tol, int max_sweeps, cudaStream_t st);

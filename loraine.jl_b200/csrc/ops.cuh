@@ -63,6 +63,16 @@ struct Reducer {
     const double* fetch(cudaStream_t st);
 };
 
+// Column ownership of the Schur matrix in multi-GPU runs: 1-D block-cyclic by column panels of width `pw`
+// (panel p -> rank p % world).  world <= 1: everything is owned.
+struct ColOwner {
+    int rank = 0, world = 1, pw = 512;
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    bool owns(int col) const { return world <= 1 || ((col / pw) % world) == rank; }
+};
+
 // ---- sparse data of one PSD block --------------------------------------------------------------------------------
 struct SparseBlock {
     int m = 0, n_var = 0;
@@ -95,9 +105,11 @@ void sp_A_vec(cudaStream_t st, const SparseBlock& sb, const double* M, int ld, d
 void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int ldg, double* BG, int ldo);
 // Sparse-pair Schur term (F3 formula, src/makeBBBB.jl:139-213 / _dot :39-64): for participating positions jj <= kk, both >= first,
 //   H[max(j,k), min(j,k)] += tr(calA_j W calA_k W)
-void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh);
+void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh,
+                    ColOwner own = ColOwner());
 // F1 column (src/makeBBBB.jl:81-104): given U = W calA_j W dense, H[max(j,k),min(j,k)] += <calA_k, U> for positions kk >= jj
-void sp_schur_f1_column(cudaStream_t st, const SparseBlock& sb, int jj, const double* U, int ldu, double* H, int ldh);
+void sp_schur_f1_column(cudaStream_t st, const SparseBlock& sb, int jj, const double* U, int ldu, double* H, int ldh,
+                        ColOwner own = ColOwner());
 // densify calA_j into a zeroed m x m buffer
 void sp_densify(cudaStream_t st, const SparseBlock& sb, int j, double* out, int ld);
 
@@ -115,7 +127,7 @@ void lin_CT_y(cudaStream_t st, const SparseLin& L, const double* y, double scale
 // out[j] += scale * sum_r C[j,r] x[r]
 void lin_C_x(cudaStream_t st, const SparseLin& L, const double* x, double scale, double* out);
 // H[j,k] += sum_r C[j,r] d[r] C[k,r]   for k <= j              (src/predictor_corrector.jl:36-38)
-void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh);
+void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh, ColOwner own = ColOwner());
 // diag[j] += sum_r C[j,r]^2 d[r]
 void lin_schur_diag(cudaStream_t st, const SparseLin& L, const double* d, double* diag);
 

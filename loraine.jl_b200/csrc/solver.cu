@@ -2,6 +2,7 @@
 // include/loraine_b200.h.  No CPU fallback: all arithmetic of the hot path runs in the kernels of gemm.cu / chol.cu /
 // eig.cu / ops.cu and in the small kernels below.
 #include "solver.cuh"
+#include "dist.cuh"
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -556,20 +557,16 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             zero_strict_upper(B.LS.p(), m, ld, st);
             // CC = L_S' L_X                                                   (src/prepare_W.jl:39)
             gemm_tn(st, m, m, m, 1.0, B.LS.p(), ld, B.LX.p(), ld, 0.0, B.T1.p(), ld);
-            // U*D, V, D = svd(CC)                                             (src/prepare_W.jl:42)
+            // U*D, D = svd(CC) without accumulating V                            (src/prepare_W.jl:42)
             {
                 Phase ps(h, LRN_T_SVD);
-                h->stat_svd_sweeps = svd_block_jacobi(B.T1.p(), ld, m, B.T2.p(), ld, B.T3.p(), ld, B.D.p, B.svd, svd_tol, 30, st);
+                h->stat_svd_sweeps = svd_block_jacobi(B.T1.p(), ld, m, B.T2.p(), ld, nullptr, 0, B.D.p, B.svd, svd_tol, 30, st);
             }
             vec_op(st, m, VEC_RSQRT, B.dm12.p, B.D.p, nullptr);
             vec_op(st, m, VEC_POW_M32, B.dm32.p, B.D.p, nullptr);
-            // G = L_X V D^{-1/2}                                              (src/prepare_W.jl:60)
-            {
-                GemmParams p;
-                p.A = B.LX.p(); p.B = B.T3.p(); p.C = B.G.p(); p.M = m; p.N = m; p.K = m; p.lda = ld; p.ldb = ld; p.ldc = ld;
-                p.colscale = B.dm12.p;
-                gemm(p, st);
-            }
+            // G = L_X V D^{-1/2} = L_S^{-T} (U D) D^{-1/2}   (CC V = U D with CC = L_S' L_X)   (src/prepare_W.jl:60)
+            mat_scale_cols(st, m, m, B.G.p(), ld, B.T2.p(), ld, B.dm12.p);
+            trsm_left_lower_trans(B.LS.p(), m, ld, B.cholS, B.G.p(), ld, m, st);
             // Gi = inv(G) = D^{-1/2} U' L_S' = (L_S (U D) D^{-3/2})'          (src/prepare_W.jl:63, closed form)
             {
                 GemmParams p;
@@ -622,6 +619,8 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
         cudaStream_t st = h->st;
         const int n = h->n_var;
         LRN_CUDA(cudaMemsetAsync(h->H.p(), 0, h->H.bytes(), st));
+        ColOwner own;                                  // multi-GPU: every rank assembles only the column panels it owns
+        own.rank = h->rank; own.world = h->world; own.pw = h->dist_pw;
         for (auto& B : h->blk) {
             const int m = B.m, ld = B.ld;
             if (h->opt.datarank == -1) {
@@ -631,7 +630,18 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
                 p.A = h->BG.p(); p.B = h->BG.p(); p.C = h->H.p();
                 p.M = n; p.N = n; p.K = m; p.lda = h->BG.ld; p.ldb = h->BG.ld; p.ldc = h->H.ld;
                 p.transB = true; p.alpha = 1.0; p.beta = 1.0; p.mode = 1; p.lower = 1;
-                gemm(p, st);
+                if (h->world <= 1) {
+                    gemm(p, st);
+                } else {
+                    for (int q0 = 0; q0 < n; q0 += own.pw) {
+                        if (!own.owns(q0)) continue;
+                        GemmParams q = p;
+                        q.lower = 0;
+                        q.A = h->BG.p() + q0; q.B = h->BG.p() + q0; q.C = h->H.p() + (size_t)q0 * h->H.ld + q0;
+                        q.M = n - q0; q.N = std::min(own.pw, n - q0);
+                        gemm(q, st);
+                    }
+                }
             } else {
                 for (int jj = 0; jj < B.sp.nF1; jj++) {
                     // F1: U = W calA_j W, column of <calA_k, U>                (src/makeBBBB.jl:81-104)
@@ -639,16 +649,16 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
                     sp_densify(st, B.sp, B.sp.h_part[jj], B.T1.p(), ld);
                     gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
                     gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.W.p(), ld, 0.0, B.T3.p(), ld);
-                    sp_schur_f1_column(st, B.sp, jj, B.T3.p(), ld, h->H.p(), h->H.ld);
+                    sp_schur_f1_column(st, B.sp, jj, B.T3.p(), ld, h->H.p(), h->H.ld, own);
                 }
                 // F3 for the remaining (sparse) matrices                       (src/makeBBBB.jl:139-213)
-                sp_schur_pairs(st, B.sp, B.sp.nF1, B.W.p(), ld, h->H.p(), h->H.ld);
+                sp_schur_pairs(st, B.sp, B.sp.nF1, B.W.p(), ld, h->H.p(), h->H.ld, own);
             }
         }
         if (h->nlin > 0) {
             // BBBB += C_lin * spdiagm(X_lin .* S_lin_inv) * C_lin'             (src/predictor_corrector.jl:36-38)
             vec_op(st, h->nlin, VEC_MUL, h->tl1.p, h->x_lin.p, h->si_lin.p);
-            lin_schur(st, h->lin, h->tl1.p, h->H.p(), h->H.ld);
+            lin_schur(st, h->lin, h->tl1.p, h->H.p(), h->H.ld, own);
         }
         h->have_factor = false;
         return LRN_OK;
@@ -709,7 +719,10 @@ int32_t lrn_schur_factor(lrn_handle_t h) {
             Phase ph(h, LRN_T_FACTOR);
             cudaStream_t st = h->st;
             LRN_CUDA(cudaMemcpyAsync(h->L.p(), h->H.p(), h->H.bytes(), cudaMemcpyDeviceToDevice, st));
-            cholesky_lower(h->L.p(), h->n_var, h->L.ld, h->cholH, st);
+            if (h->world > 1)
+                cholesky_dist(h->L.p(), h->n_var, h->L.ld, h->cholH, *static_cast<DistCtx*>(h->nccl), h->dist_pw, h->panelbuf, st);
+            else
+                cholesky_lower(h->L.p(), h->n_var, h->L.ld, h->cholH, st);
             LRN_CUDA(cudaMemcpyAsync(&info, h->cholH.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
             LRN_CUDA(cudaStreamSynchronize(st));
         }
@@ -924,6 +937,8 @@ int32_t lrn_get_array(lrn_handle_t h, int32_t which, int64_t iblk, double* out) 
             LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
             DMat& M = (which == LRN_ARR_H) ? h->H : h->L;
             // work on a copy in tn-sized chunks is not possible: use the spare matrix of the other kind only when safe
+            if (which == LRN_ARR_H && h->world > 1)      // every rank holds only its own column panels: sum them up
+                dist_allreduce_sum(M.p(), (size_t)M.ld * n, *static_cast<DistCtx*>(h->nccl), st);
             if (which == LRN_ARR_H) mat_mirror_lower(st, n, M.p(), M.ld);
             else zero_strict_upper(M.p(), n, M.ld, st);
             download_dense(h, M.p(), M.ld, n, n, out);

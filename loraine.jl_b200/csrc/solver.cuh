@@ -79,5 +79,7 @@ struct lrn_solver {
     int prec_ready = 0;                // kind prepared (0 none)
     // distributed
     int rank = 0, world = 1;
-    void* nccl = nullptr;
+    void* nccl = nullptr;              // lrn::DistCtx*
+    int dist_pw = 512;                 // column panel width of the block-cyclic Schur distribution
+    lrn::DevBuf<double> panelbuf;
 };
