@@ -84,9 +84,24 @@ def dist_env():
     return rank, world, local
 
 
-def algorithmic_flops(n_var, m, nnzB):
-    """rank-one assembly n_var^2 m (lower SYRK, 2 flop/MAC) + 2 nnz(B) m + n_var^2/2 ; Cholesky n_var^3/3"""
-    return dict(assemble=float(n_var) ** 2 * m + 2.0 * nnzB * m + 0.5 * float(n_var) ** 2, factor=float(n_var) ** 3 / 3.0)
+def algorithmic_flops(md, datarank):
+    """SURVEY 8(d).  Rank-one assembly: sum_i n_var^2 m_i (lower SYRK, 2 flop/MAC) + 2 nnz(B_i) m_i + n_var^2/2.
+    General assembly: sum_i sum_j min(F1_j, F3_j), F1_j = 2 m nnz_j + 2 m^3 + 2 sum_{k>=j} nnz_k, F3_j = 4 nnz_j sum_{k>=j} nnz_k
+    (k over the matrices present in block i in sigmaA order).  Cholesky: n_var^3 / 3."""
+    n = float(md.n)
+    asm = 0.0
+    for i, m in enumerate(md.msizes):
+        if datarank == -1 and md.B:
+            asm += n * n * m + 2.0 * md.B[i].nnz * m + 0.5 * n * n
+        else:
+            nz = np.sort(md.nzA[:, i][md.nzA[:, i] > 0])[::-1].astype(np.float64)
+            suf = np.cumsum(nz[::-1])[::-1]
+            f1 = 2.0 * m * nz + 2.0 * float(m) ** 3 + 2.0 * suf
+            f3 = 4.0 * nz * suf
+            asm += float(np.minimum(f1, f3).sum())
+    if md.nlin:
+        asm += 2.0 * float((np.diff(md.C_lin.tocsc().indptr).astype(np.float64) ** 2).sum())
+    return dict(assemble=asm, factor=n ** 3 / 3.0)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -145,7 +160,10 @@ def run_reference(args):
 
 
 def workload_name(w):
-    return {"C2": "configs[1]: synthetic Max-Cut SDP (ex_maxcut.jl / maxG11 layout) n=5000, 1 PSD block m=5000, datarank=-1 rank-one "
+    return {"C5": "configs[4]: synthetic large-Schur SDP n_var=40000 constraints, 1 PSD block m=1000, kit=0, datarank=0 (seed 40000)",
+            "C4": "configs[3]: synthetic multi-block SDP, 50 PSD blocks of size 200 + LP block of 2000 rows, n_var=10000, kit=0",
+            "C3": "configs[2]: synthetic Lovasz-theta SDP (thetaG11 layout) m=801, n_var=2401, kit=1 CG, preconditioner=1",
+            "C2": "configs[1]: synthetic Max-Cut SDP (ex_maxcut.jl / maxG11 layout) n=5000, 1 PSD block m=5000, datarank=-1 rank-one "
                   "Schur path, kit=0 (torus 50x100, +-1 weights, seed 5000)"}.get(w, w)
 
 
@@ -174,6 +192,9 @@ def run_b200(args):
     opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
     s, ha = opt.solver, opt.halpha
     S.setup_solver(s, ha)
+    sharded = False
+    if world > 1 and args.workload.startswith("C5"):
+        sharded = pkg.dist.init_distributed(s)      # Schur assembly + Cholesky sharded over the ranks (NCCL panel broadcast)
     S.initial_point(s)
     md = s.model
 
@@ -261,19 +282,22 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    sec_per_iter = t_dev / (args.steps * world)
-    e2e_val = t_e2e / (e2e_steps * world)
-    nnzB = md.B[0].nnz if md.B else 0
-    alg = algorithmic_flops(md.n, md.msizes[0] if md.nlmi else 0, nnzB)
+    # replicas: the job advances `world` independent solves per step; sharded: all ranks advance ONE solve together
+    units = 1 if sharded else world
+    sec_per_iter = t_dev / (args.steps * units)
+    e2e_val = t_e2e / (e2e_steps * units)
+    alg = algorithmic_flops(md, int(s.datarank))
     asm_ms = phase["schur_assemble"][0] / max(1, phase["schur_assemble"][1])
     fac_ms = phase["schur_factor"][0] / max(1, phase["schur_factor"][1])
     achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
     line = dict(
         metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-        ms_per_step=1e3 * t_dev / args.steps, higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        ms_per_step=1e3 * t_dev / args.steps, higher_is_better=False, scaling="strong" if sharded else "weak", vs_baseline=None,
+        dtype="f64", data="synthetic",
         config=dict(workload=workload_name(args.workload), n_var=md.n, msizes=md.msizes[:4], nlin=md.nlin,
                     options=cfg["options"], l2="inputs larger than L2 (every dense operand is 200 MB; 21 resident m x m matrices)",
-                    parallelism="replicas only" if world > 1 else "single GPU"),
+                    parallelism=("schur assembly + Cholesky sharded block-cyclic over %d GPUs (NCCL panel broadcast), rest replicated" % world)
+                    if sharded else ("replicas only" if world > 1 else "single GPU")),
         e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=e2e_steps),
         gpu_launches=int(launches),
         clocks=clocks,
@@ -307,6 +331,13 @@ def cpu_baseline(pkg, args):
         scale = (5000.0 / (rows * cols)) ** 3
         note = (f"1 IP iteration (after 1 warm-up iteration) of the same generator at torus {rows}x{cols} (n = m = {rows * cols}); all phases are "
                 f"O(n^3): seconds scaled by (5000/{rows * cols})^3 = {scale:.0f} to the full size (explicit extrapolation)")
+    elif args.workload == "C5":
+        ns = 4000
+        arrays = pkg.problems.large_schur(1000, ns, 40000)
+        scale = (40000.0 / ns) ** 3
+        note = (f"1 IP iteration (after 1 warm-up iteration) of the same generator at reduced n_var = {ns} (m = 1000 kept); the "
+                f"iteration is dominated by the n_var^3/3 Cholesky and the O(n_var^2) pair assembly: seconds scaled by "
+                f"(40000/{ns})^3 = {scale:.0f} (explicit extrapolation, upper estimate)")
     else:
         arrays = cfg["gen"]()
     o = dict(cfg["options"], verb=0)

@@ -116,7 +116,55 @@ void panel_trsm(double* P, int rows, int kb, const double* Akk, const double* dk
     }
 }
 
-void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, cudaStream_t st) {
+__global__ void k_copy2d(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i < rows && j < cols) dst[(size_t)j * ldd + i] = src[(size_t)j * lds + i];
+}
+void copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)cdiv(rows, 256), (unsigned)cols);
+    k_copy2d<<<grid, 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+    LRN_CHECK_LAUNCH();
+}
+
+// X = inv(L_kk) (kb x kb lower, leading dimension ldx) from the factor and its inverted 64x64 diagonal blocks:
+// block row i:  X[i, 0:i) = -inv(L_ii) * ( L[i, 0:i) * X[0:i, 0:i) ),  X[i,i] = inv(L_ii).   2 small GEMMs per block row.
+void trtri_blocked(const double* Lkk, int kb, int lda, const double* dk, double* X, int ldx, double* T, cudaStream_t st) {
+    LRN_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * kb * sizeof(double), st));
+    const int nb = (int)cdiv(kb, DB);
+    for (int i = 0; i < nb; i++) {
+        const int i0 = i * DB, ib = (kb - i0 < DB) ? (kb - i0) : DB;
+        const double* di = dk + (size_t)i * DB * DB;
+        copy2d(di, DB, X + (size_t)i0 * ldx + i0, ldx, ib, ib, st);
+        if (i > 0) {
+            gemm_nn(st, ib, i0, i0, 1.0, Lkk + i0, lda, X, ldx, 0.0, T, DB);
+            gemm_nn(st, ib, i0, ib, -1.0, di, DB, T, DB, 0.0, X + i0, ldx);
+        }
+    }
+}
+
+// rows below a factored kb x kb diagonal block: P <- P * inv(L_kk)^T as ONE large GEMM through the explicit inverse
+// (out of place into work.pout or the caller's buffer, then copied back)
+void panel_trsm_inv(double* P, int rows, int kb, const double* Akk, const double* dk, int lda, CholWork& work, double* Pout,
+                    int ldp, cudaStream_t st) {
+    const int ldx = pad_ld(kb);
+    const size_t need = (size_t)ldx * kb + (size_t)DB * kb;
+    if (work.xinv.n < need) work.xinv.alloc(need);
+    double* X = work.xinv.p;
+    double* T = X + (size_t)ldx * kb;
+    trtri_blocked(Akk, kb, lda, dk, X, ldx, T, st);
+    double* out = Pout;
+    int ldo = ldp;
+    if (!out) {
+        ldo = pad_ld(rows);
+        if (work.pout.n < (size_t)ldo * kb) work.pout.alloc((size_t)ldo * kb);
+        out = work.pout.p;
+    }
+    gemm_nt(st, rows, kb, kb, 1.0, P, lda, X, ldx, 0.0, out, ldo);
+    copy2d(out, ldo, P, lda, rows, kb, st);
+}
+
+void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, CholWork& work, cudaStream_t st) {
     if (n <= DB) {
         potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(A, lda, n, dinv, info, base);
         LRN_CHECK_LAUNCH();
@@ -127,11 +175,12 @@ void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, cuda
         const int kb = (n - k < NB) ? (n - k) : NB;
         double* Akk = A + (size_t)k * lda + k;
         double* dk = dinv + (size_t)(k / DB) * DB * DB;
-        chol_rec(Akk, kb, lda, dk, info, base + k, st);
+        chol_rec(Akk, kb, lda, dk, info, base + k, work, st);
         const int rows = n - k - kb;
         if (rows <= 0) break;
         double* P = A + (size_t)k * lda + (k + kb);          // rows x kb panel below the diagonal block
-        panel_trsm(P, rows, kb, Akk, dk, lda, st);
+        if (kb >= 128 && rows >= 1024) panel_trsm_inv(P, rows, kb, Akk, dk, lda, work, nullptr, 0, st);
+        else panel_trsm(P, rows, kb, Akk, dk, lda, st);
         // trailing update, lower triangle only
         GemmParams p;
         p.A = P; p.B = P; p.C = A + (size_t)(k + kb) * lda + (k + kb);
@@ -197,14 +246,22 @@ __global__ void zero_upper_kernel(double* A, int n, int lda) {
 
 }  // namespace
 
-void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, cudaStream_t st) {
+void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
+                    int ldp, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
         configured = true;
     }
-    chol_rec(Apanel, w, lda, dinv, info, base, st);
-    if (rows > w) panel_trsm(Apanel + w, rows - w, w, Apanel, dinv, lda, st);
+    chol_rec(Apanel, w, lda, dinv, info, base, work, st);
+    if (rows > w) {
+        if (w >= 128 && rows - w >= 1024) panel_trsm_inv(Apanel + w, rows - w, w, Apanel, dinv, lda, work, Pout ? Pout + w : nullptr, ldp, st);
+        else {
+            panel_trsm(Apanel + w, rows - w, w, Apanel, dinv, lda, st);
+            if (Pout) copy2d(Apanel + w, lda, Pout + w, ldp, rows - w, w, st);
+        }
+    }
+    if (Pout) copy2d(Apanel, lda, Pout, ldp, w, w, st);
 }
 
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st) {
@@ -216,7 +273,7 @@ void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st) 
     }
     LRN_CUDA(cudaMemsetAsync(work.info_ptr(), 0, sizeof(int), st));
     if (n <= 0) return;
-    chol_rec(A, n, lda, work.dinv.p, work.info_ptr(), 0, st);
+    chol_rec(A, n, lda, work.dinv.p, work.info_ptr(), 0, work, st);
 }
 
 void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {

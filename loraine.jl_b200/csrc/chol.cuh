@@ -13,6 +13,10 @@ struct CholWork {
     DevBuf<double> dinv;      // cdiv(n,64) blocks of 64x64 (ld 64), zero above the diagonal
     DevBuf<int> info;         // [0] = 0 ok, >0 = 1-based index of the first non-positive pivot (LAPACK convention)
     int* info_ext = nullptr;  // optional external flag location (lets the caller gather many flags with one copy)
+    DevBuf<double> xinv;      // inverse of the current panel's diagonal block (kb x kb) + 64 x kb scratch
+    DevBuf<double> pout;      // out-of-place panel solve result (rows x kb)
+    cudaStream_t aux = nullptr;   // high-priority side stream (panel factorisation + broadcast look-ahead in multi-GPU runs)
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n = 0;
     void ensure(int n_) {
         if (n_ > n || !dinv.p) { dinv.alloc((size_t)cdiv(n_, CHOL_DB) * CHOL_DB * CHOL_DB); n = n_; }
@@ -27,7 +31,10 @@ void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st);
 
 // Factor one column panel: the w x w diagonal block at the top of `Apanel` (rows x w) and the TRSM of the rows below it.
 // `dinv` points at the 64x64 inverse blocks of this panel, `base` is the global index of its first column (for info).
-void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, cudaStream_t st);
+// If `Pout` is non-null the solved rows (below the diagonal block) are ALSO written to Pout + w (leading dimension ldp)
+// and the diagonal block is copied to Pout (packed panel for a broadcast).
+void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
+                    int ldp, cudaStream_t st);
 
 // x <- L^{-1} x (which=1), x <- L^{-T} x (which=2), both (which=3). `tmp` has n doubles. Uses work.dinv of the same factor.
 void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st);

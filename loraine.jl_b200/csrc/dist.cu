@@ -49,46 +49,67 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
     work.ensure(n);
     LRN_REQUIRE(pw % CHOL_DB == 0, "panel width must be a multiple of 64");
     const int npan = (int)cdiv(n, pw), ldp = pad_ld(n);
-    const size_t need = (size_t)ldp * pw + (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB + 8;
-    if (panelbuf.n < need) panelbuf.alloc(need);
+    const size_t ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
+    const size_t bufsz = (size_t)ldp * pw + ndmax + 8;
+    if (panelbuf.n < 2 * bufsz) panelbuf.alloc(2 * bufsz);
+    if (!work.aux) {
+        int lo = 0, hi = 0;
+        LRN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        LRN_CUDA(cudaStreamCreateWithPriority(&work.aux, cudaStreamNonBlocking, hi));
+        for (auto& e : work.ev) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t sp = work.aux;                     // panel stream: factor panel p+1 and broadcast it while `st` still
+    cudaEvent_t evStart = work.ev[0], evU = work.ev[1];   // applies the trailing updates of panel p (one-step look-ahead)
+    cudaEvent_t evB[2] = {work.ev[2], work.ev[3]}, evE[2] = {work.ev[4], work.ev[5]};
     int* info = work.info_ptr();
     LRN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    LRN_CUDA(cudaEventRecord(evStart, st));
+    LRN_CUDA(cudaStreamWaitEvent(sp, evStart, 0));
+    LRN_CUDA(cudaEventRecord(evU, st));
     for (int p = 0; p < npan; p++) {
+        const int b = p & 1;
         const int c0 = p * pw, w = (n - c0 < pw) ? (n - c0) : pw, rows = n - c0, owner = p % ctx.world;
+        double* buf = panelbuf.p + (size_t)b * bufsz;
         double* Ap = A + (size_t)c0 * lda + c0;
         double* dk = work.dinv.p + (size_t)(c0 / CHOL_DB) * CHOL_DB * CHOL_DB;
         const int nd = (int)cdiv(w, CHOL_DB) * CHOL_DB * CHOL_DB;
-        double* dbuf = panelbuf.p + (size_t)ldp * pw;
-        dim3 grid((unsigned)cdiv(rows, 256), (unsigned)w);
+        double* dbuf = buf + (size_t)ldp * pw;
+        if (p >= 2) LRN_CUDA(cudaStreamWaitEvent(sp, evE[b], 0));      // buffer b was last read by the updates of step p-2
         if (ctx.rank == owner) {
-            cholesky_panel(Ap, rows, w, lda, dk, info, c0, st);
-            k_pack_panel<<<grid, 256, 0, st>>>(Ap, lda, rows, w, panelbuf.p, ldp, 0);
-            LRN_CHECK_LAUNCH();
-            LRN_CUDA(cudaMemcpyAsync(dbuf, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));                    // panel p has received the update of step p-1
+            cholesky_panel(Ap, rows, w, lda, dk, info, c0, work, buf, ldp, sp);   // factor + pack
+            LRN_CUDA(cudaMemcpyAsync(dbuf, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
         }
-        // one broadcast carries the panel and the inverse diagonal blocks (contiguous in panelbuf)
-        LRN_NCCL(nccl_api().Broadcast(panelbuf.p, panelbuf.p, (size_t)ldp * pw + nd, ncclDouble, owner, ctx.comm, st));
-        if (ctx.rank != owner) {
-            k_pack_panel<<<grid, 256, 0, st>>>(Ap, lda, rows, w, panelbuf.p, ldp, 1);
+        // one broadcast carries the panel and its inverse diagonal blocks (contiguous in buf)
+        LRN_NCCL(nccl_api().Broadcast(buf, buf, (size_t)ldp * pw + nd, ncclDouble, owner, ctx.comm, sp));
+        LRN_CUDA(cudaEventRecord(evB[b], sp));
+        LRN_CUDA(cudaStreamWaitEvent(st, evB[b], 0));
+        if (ctx.rank != owner) {                                          // every rank keeps the complete factor
+            dim3 grid((unsigned)cdiv(rows, 256), (unsigned)w);
+            k_pack_panel<<<grid, 256, 0, st>>>(Ap, lda, rows, w, buf, ldp, 1);
             LRN_CHECK_LAUNCH();
             LRN_CUDA(cudaMemcpyAsync(dk, dbuf, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
         }
-        for (int q = p + 1; q < npan; q++) {
-            if (q % ctx.world != ctx.rank) continue;
+        auto update = [&](int q) {
             const int q0 = q * pw, wq = (n - q0 < pw) ? (n - q0) : pw;
-            const double* Pq = panelbuf.p + (q0 - c0);
+            const double* Pq = buf + (q0 - c0);
             gemm_nt(st, n - q0, wq, w, -1.0, Pq, ldp, Pq, ldp, 1.0, A + (size_t)q0 * lda + q0, lda);
+        };
+        if (p + 1 < npan && (p + 1) % ctx.world == ctx.rank) {            // next panel first, so that its owner can go on
+            update(p + 1);
+            LRN_CUDA(cudaEventRecord(evU, st));
         }
+        for (int q = p + 2; q < npan; q++)
+            if (q % ctx.world == ctx.rank) update(q);
+        LRN_CUDA(cudaEventRecord(evE[b], st));
     }
     // the first failing pivot index is known to the owner of that panel only: take the smallest non-zero over ranks
-    DevBuf<int>& tmp = work.info;   // scratch int lives next to the flag when an external flag is used
     int* all = nullptr;
     LRN_CUDA(cudaMalloc(&all, sizeof(int) * ctx.world));
     LRN_NCCL(nccl_api().AllGather(info, all, 1, ncclInt32, ctx.comm, st));
     for (int r = 0; r < ctx.world; r++) k_max_int<<<1, 1, 0, st>>>(info, all + r);
     LRN_CUDA(cudaStreamSynchronize(st));
     cudaFree(all);
-    (void)tmp;
 }
 
 }  // namespace lrn

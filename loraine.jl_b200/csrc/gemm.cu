@@ -15,8 +15,6 @@ namespace lrn {
 
 namespace {
 
-constexpr int BK = 16;
-constexpr int STAGES = 4;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -39,7 +37,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // Load one operand tile (BMN x BK of op(X)) into shared memory.
 //   CONTIG_MN = true : global element (r,k) at X[r + k*ld]  -> smem [k][r] with row stride BMN+4
 //   CONTIG_MN = false: global element (r,k) at X[k + r*ld]  -> smem [r][k] with row stride BK+4
-template <int BMN, int NT, bool CONTIG_MN, bool ALIGN16>
+template <int BMN, int BK, int NT, bool CONTIG_MN, bool ALIGN16>
 __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ X, int ld, int r0, int k0,
                                           int R, int K, int tid) {
     if (CONTIG_MN) {
@@ -91,21 +89,22 @@ __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* 
     }
 }
 
-template <int BM, int BN>
+template <int BM, int BN, int BK, int STAGES>
 struct TileSmem {
-    static constexpr int A_ELEMS = BM * (BK + 4);   // >= BK*(BM+4) for BM >= 16
-    static constexpr int B_ELEMS = BN * (BK + 4);
+    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+    static constexpr int A_ELEMS = cmax(BM * (BK + 4), BK * (BM + 4));
+    static constexpr int B_ELEMS = cmax(BN * (BK + 4), BK * (BN + 4));
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
     static constexpr size_t BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
 };
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, bool ALIGN16>
+template <int BM, int BN, int BK, int STAGES, int WARPS_M, int WARPS_N, bool TA, bool TB, bool ALIGN16>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     dgemm_dmma_kernel(const GemmParams p) {
     constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MI = WM / 8, NI = WN / 8;
-    using SM = TileSmem<BM, BN>;
+    using SM = TileSmem<BM, BN, BK, STAGES>;
     extern __shared__ __align__(16) double smem[];
 
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -132,9 +131,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
         double* sA = smem + (size_t)(kt % STAGES) * SM::STAGE_ELEMS;
         double* sB = sA + SM::A_ELEMS;
         // op(A) is M x K: !TA -> contiguous along M; TA -> contiguous along K
-        load_tile<BM, NT, !TA, ALIGN16>(sA, A, p.lda, m0, kt * BK, p.M, Kz, tid);
+        load_tile<BM, BK, NT, !TA, ALIGN16>(sA, A, p.lda, m0, kt * BK, p.M, Kz, tid);
         // op(B) is K x N: !TB -> contiguous along K; TB -> contiguous along N
-        load_tile<BN, NT, TB, ALIGN16>(sB, B, p.ldb, n0, kt * BK, p.N, Kz, tid);
+        load_tile<BN, BK, NT, TB, ALIGN16>(sB, B, p.ldb, n0, kt * BK, p.N, Kz, tid);
     };
 
 #pragma unroll
@@ -207,11 +206,11 @@ constexpr size_t PROF_CAP = 60000;
 std::atomic<long long> g_kernel_launches{0};
 namespace {
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, bool AL>
+template <int BM, int BN, int BK, int STAGES, int WARPS_M, int WARPS_N, bool TA, bool TB, bool AL>
 void launch_cfg(const GemmParams& p, cudaStream_t st) {
-    auto kern = dgemm_dmma_kernel<BM, BN, WARPS_M, WARPS_N, TA, TB, AL>;
+    auto kern = dgemm_dmma_kernel<BM, BN, BK, STAGES, WARPS_M, WARPS_N, TA, TB, AL>;
     static bool configured = false;
-    constexpr size_t smem = TileSmem<BM, BN>::BYTES;
+    constexpr size_t smem = TileSmem<BM, BN, BK, STAGES>::BYTES;
     if (!configured) {
         LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -240,9 +239,9 @@ void launch_shape(const GemmParams& p, cudaStream_t st) {
     long long tilesL = cdiv(p.M, 128) * cdiv(p.N, 128) * (long long)p.batch * p.batch2;
     if (p.lower) tilesL = tilesL / 2 + cdiv(p.M, 128);
     if (tilesL >= 100 && p.M > 64 && p.N > 64)
-        launch_cfg<128, 128, 2, 4, TA, TB, AL>(p, st);
+        launch_cfg<128, 128, 32, 3, 2, 4, TA, TB, AL>(p, st);
     else
-        launch_cfg<64, 64, 2, 2, TA, TB, AL>(p, st);
+        launch_cfg<64, 64, 16, 4, 2, 2, TA, TB, AL>(p, st);
 }
 
 template <bool AL>
