@@ -23,6 +23,8 @@ int32_t lrn_dbg_svd(int32_t m, const double* A, double* UD, double* V, double* s
 /* Lanczos extreme eigenpairs of the symmetric m x m matrix T */
 int32_t lrn_dbg_lanczos(int32_t m, const double* T, int32_t nev_top, double tol, double* lmin, double* lmax,
                         double* top_vals, double* top_vecs, int32_t* iters, int32_t* converged);
+/* batched smallest eigenvalue of `count` symmetric m x m matrices stored one after the other (tridiagonalisation kernel) */
+int32_t lrn_dbg_batched_lambda_min(int32_t count, int32_t m, const double* mats, double* out);
 /* device micro-benchmarks: kind 0 = DMMA (mma.sync m8n8k4 f64) register-resident peak, 1 = DFMA peak, 2 = HBM copy GB/s */
 int32_t lrn_dbg_peak(int32_t kind, double* value);
 

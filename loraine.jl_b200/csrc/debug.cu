@@ -5,6 +5,7 @@
 #include "eig.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
+#include <memory>
 
 using namespace lrn;
 
@@ -205,6 +206,24 @@ int32_t lrn_dbg_lanczos(int32_t m, const double* T, int32_t nev_top, double tol,
             for (int t = 0; t < nev_top; t++) top_vals[t] = tv[t];
             dV.download(top_vecs);
         }
+        return LRN_OK;
+    });
+}
+
+int32_t lrn_dbg_batched_lambda_min(int32_t count, int32_t m, const double* mats, double* out) {
+    return guard([&]() -> int32_t {
+        std::vector<std::unique_ptr<HostMat>> hm;
+        std::vector<double*> ptrs; std::vector<int> ms, lds;
+        for (int z = 0; z < count; z++) {
+            hm.emplace_back(new HostMat(mats + (size_t)z * m * m, m, m));
+            ptrs.push_back(hm.back()->p); ms.push_back(m); lds.push_back(hm.back()->ld);
+        }
+        DevBuf<double*> dp; DevBuf<int> dm, dl; DevBuf<double> dout(count);
+        dp.upload(ptrs); dm.upload(ms); dl.upload(lds);
+        LRN_CUDA(cudaDeviceSynchronize());
+        batched_lambda_min(dp.p, dm.p, dl.p, count, dout.p, 0);
+        LRN_CUDA(cudaDeviceSynchronize());
+        LRN_CUDA(cudaMemcpy(out, dout.p, count * sizeof(double), cudaMemcpyDeviceToHost));
         return LRN_OK;
     });
 }

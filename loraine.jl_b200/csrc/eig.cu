@@ -219,6 +219,32 @@ __global__ void svd_gather_kernel(const double* __restrict__ W, int ldw, int m, 
     if (i == 0) sigma[r] = sv[src];
 }
 
+__global__ void svd_init_batched_kernel(const double* const* __restrict__ A, int lda, int m, int mp, double* __restrict__ W, int ldw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, b = blockIdx.z;
+    if (i >= m) return;
+    W[((size_t)b * mp + j) * ldw + i] = (j < m) ? A[b][(size_t)j * lda + i] : 0.0;
+}
+__global__ void rank_desc_batched_kernel(const double* __restrict__ v, int n, int* __restrict__ perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= n) return;
+    const double* vb = v + (size_t)b * n;
+    double vi = vb[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        double vj = vb[j];
+        if (vj > vi || (vj == vi && j < i)) rank++;
+    }
+    perm[(size_t)b * n + rank] = i;
+}
+__global__ void svd_gather_batched_kernel(const double* __restrict__ W, int ldw, int m, int mp, const int* __restrict__ perm,
+                                          const double* __restrict__ sv, double* const* __restrict__ UD, int ldu,
+                                          double* const* __restrict__ sigma) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, b = blockIdx.z;
+    int src = perm[(size_t)b * mp + r];
+    if (i < m) UD[b][(size_t)r * ldu + i] = W[((size_t)b * mp + src) * ldw + i];
+    if (i == 0) sigma[b][r] = sv[(size_t)b * mp + src];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Lanczos kernels
 // ---------------------------------------------------------------------------------------------------------------
@@ -284,7 +310,126 @@ __global__ void __launch_bounds__(1024) lanczos_beta_kernel(const double* __rest
     if (threadIdx.x == 0) scal[1] = beta;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// batched Householder tridiagonalisation + Sturm multisection (one CTA per matrix)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TRD_T = 512;       // threads
+constexpr int TRD_MAXM = 1024;   // v, p vectors in shared memory
+
+__global__ void __launch_bounds__(TRD_T) k_batched_lambda_min(double* const* __restrict__ mats, const int* __restrict__ ms,
+                                                               const int* __restrict__ lds, double* __restrict__ out) {
+    __shared__ double v[TRD_MAXM], pv[TRD_MAXM], d[TRD_MAXM], e[TRD_MAXM];
+    __shared__ double red[32];
+    __shared__ double s_alpha, s_beta, s_lo, s_hi;
+    __shared__ int cnt[TRD_T + 1];
+    const int z = blockIdx.x, tid = threadIdx.x;
+    double* A = mats[z];
+    const int m = ms[z], ld = lds[z];
+    for (int k = 0; k < m; k++) {
+        const int r = m - k - 1;                       // length of the column below the diagonal
+        if (tid == 0) d[k] = A[(size_t)k * ld + k];
+        if (r <= 0) break;
+        double* x = A + (size_t)k * ld + k + 1;        // column k below the diagonal
+        double* A22 = A + (size_t)(k + 1) * ld + k + 1;
+        if (r == 1) {
+            if (tid == 0) e[k] = x[0];
+            __syncthreads();
+            continue;
+        }
+        // ||x||
+        double s = 0.0;
+        for (int i = tid; i < r; i += TRD_T) { double t = x[i]; v[i] = t; s += t * t; }
+        s = block_sum(s, red);
+        const double nrm = sqrt(s);
+        if (nrm == 0.0) {
+            if (tid == 0) e[k] = 0.0;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            const double x0 = v[0];
+            const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+            v[0] = x0 - alpha;
+            s_alpha = alpha;
+            s_beta = 2.0 / (s - x0 * x0 + v[0] * v[0]);
+            e[k] = alpha;
+        }
+        __syncthreads();
+        const double beta = s_beta;
+        // p = beta * A22 * v   (A22 symmetric, full storage: coalesced over rows)
+        for (int i = tid; i < r; i += TRD_T) {
+            double acc = 0.0;
+            const double* row = A22 + i;
+            for (int j = 0; j < r; j++) acc += row[(size_t)j * ld] * v[j];
+            pv[i] = beta * acc;
+        }
+        __syncthreads();
+        double pk = 0.0;
+        for (int i = tid; i < r; i += TRD_T) pk += pv[i] * v[i];
+        pk = block_sum(pk, red);
+        const double K = 0.5 * beta * pk;
+        for (int i = tid; i < r; i += TRD_T) pv[i] -= K * v[i];        // w = p - K v
+        __syncthreads();
+        // A22 <- A22 - v w' - w v'
+        for (int idx = tid; idx < r * r; idx += TRD_T) {
+            const int i = idx % r, j = idx / r;
+            A22[(size_t)j * ld + i] -= v[i] * pv[j] + pv[i] * v[j];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // Gershgorin bounds
+    double lo = 1.0e300, hi = -1.0e300;
+    for (int i = tid; i < m; i += TRD_T) {
+        double rad = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < m - 1 ? fabs(e[i]) : 0.0);
+        lo = fmin(lo, d[i] - rad);
+        hi = fmax(hi, d[i] + rad);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    __syncthreads();
+    if ((tid & 31) == 0) { red[tid >> 5] = lo; }
+    __syncthreads();
+    if (tid == 0) { double t = red[0]; for (int w = 1; w < TRD_T / 32; w++) t = fmin(t, red[w]); s_lo = t; }
+    __syncthreads();
+    if ((tid & 31) == 0) { red[tid >> 5] = hi; }
+    __syncthreads();
+    if (tid == 0) { double t = red[0]; for (int w = 1; w < TRD_T / 32; w++) t = fmax(t, red[w]); s_hi = t; }
+    __syncthreads();
+    // multisection: thread t counts eigenvalues below x_t = lo + (t+1) (hi-lo)/(T+1); the smallest eigenvalue lies in the
+    // first sub-interval whose right end has count >= 1
+    for (int round = 0; round < 12; round++) {
+        const double a = s_lo, b = s_hi;
+        const double h = (b - a) / (TRD_T + 1);
+        const double xs = a + (tid + 1) * h;
+        int c = 0;
+        double q = d[0] - xs;
+        if (q < 0.0) c++;
+        for (int i = 1; i < m; i++) {
+            if (fabs(q) < 1.0e-300) q = -1.0e-300;
+            q = d[i] - xs - e[i - 1] * e[i - 1] / q;
+            if (q < 0.0) c++;
+        }
+        cnt[tid] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int first = TRD_T;                          // index of the first shift with count >= 1
+            for (int t = 0; t < TRD_T; t++) if (cnt[t] >= 1) { first = t; break; }
+            s_lo = a + first * h;                       // left neighbour (shift index first-1 -> a + first*h)
+            s_hi = (first < TRD_T) ? a + (first + 1) * h : b;
+        }
+        __syncthreads();
+        if (!(s_hi - s_lo > 4.0e-16 * fmax(fabs(s_lo), fabs(s_hi)))) break;
+    }
+    if (tid == 0) out[z] = 0.5 * (s_lo + s_hi);
+}
+
 }  // namespace
+
+void batched_lambda_min(double* const* mats, const int* ms, const int* lds, int count, double* out, cudaStream_t st) {
+    if (count <= 0) return;
+    k_batched_lambda_min<<<count, TRD_T, 0, st>>>(mats, ms, lds, out);
+    LRN_CHECK_LAUNCH();
+}
 
 void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st) {
     LRN_REQUIRE(p.n >= 1 && p.n <= EN, "jacobi_eig_small handles n <= 64");
@@ -390,6 +535,94 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
     LRN_CHECK_LAUNCH();
     dim3 grid((unsigned)cdiv(m, 256), (unsigned)m);
     svd_gather_kernel<<<grid, 256, 0, st>>>(cur, ldw, m, w.perm.p, w.sv.p, U_D, ldu, V, ldv, sigma);
+    LRN_CHECK_LAUNCH();
+    return sweeps;
+}
+
+void SvdBatchWork::ensure(int m_, int nb_) {
+    if (m_ == m && nb_ == nb && buf0.p) return;
+    m = m_; nb = nb_;
+    mp = round_up(m, 64);
+    ldw = pad_ld(m);
+    buf0.alloc((size_t)ldw * mp * nb);
+    buf1.alloc((size_t)ldw * mp * nb);
+    const int nblk = mp / 32, pairs = nblk / 2;
+    splits = (int)std::min<long long>(16, std::max<long long>(1, cdiv(296, (long long)pairs * nb)));
+    Kc = round_up((int)cdiv(m, splits), 16);
+    if (Kc < 64) Kc = 64;
+    splits = (int)cdiv(m, Kc);
+    if (splits == 1) Kc = m;
+    gram.alloc((size_t)pairs * nb * splits * 64 * 64);
+    rot.alloc((size_t)pairs * nb * 64 * 64);
+    offmax.alloc(1);
+    sv.alloc((size_t)mp * nb);
+    perm.alloc((size_t)mp * nb);
+    std::vector<int> pi(nblk), all((size_t)nblk * nb);
+    const int h = pairs;
+    for (int s = 0; s < nblk; s++) pi[s] = s;
+    if (h > 1) {
+        pi[0] = 0;
+        for (int k = 1; k < h - 1; k++) pi[2 * k] = 2 * (k + 1);
+        pi[2 * (h - 1)] = 2 * (h - 1) + 1;
+        for (int k = 1; k < h; k++) pi[2 * k + 1] = 2 * (k - 1) + 1;
+        pi[1] = 2;
+    }
+    for (int b = 0; b < nb; b++)
+        for (int s = 0; s < nblk; s++) all[(size_t)b * nblk + s] = b * nblk + pi[s];
+    slotmap.upload(all);
+    LRN_CUDA(cudaDeviceSynchronize());
+}
+
+int svd_block_jacobi_batched(const double* const* A, int lda, int m, int nb, double* const* UD, int ldu, double* const* sigma,
+                             SvdBatchWork& w, double tol, int max_sweeps, cudaStream_t st) {
+    w.ensure(m, nb);
+    const int mp = w.mp, ldw = w.ldw, nblk = mp / 32, pairs = nblk / 2, rounds = nblk - 1;
+    const int inner = (nblk == 2) ? 40 : 1;
+    double* cur = w.buf0.p;
+    double* nxt = w.buf1.p;
+    {
+        dim3 grid((unsigned)cdiv(m, 256), (unsigned)mp, (unsigned)nb);
+        svd_init_batched_kernel<<<grid, 256, 0, st>>>(A, lda, m, mp, cur, ldw);
+        LRN_CHECK_LAUNCH();
+    }
+    const int splits = w.splits, Kc = w.Kc, np = pairs * nb;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        LRN_CUDA(cudaMemsetAsync(w.offmax.p, 0, sizeof(double), st));
+        for (int r = 0; r < rounds; r++) {
+            GemmParams g;
+            g.A = cur; g.B = cur; g.C = w.gram.p;
+            g.transA = true; g.transB = false;
+            g.M = 64; g.N = 64; g.K = Kc; g.lda = ldw; g.ldb = ldw; g.ldc = 64;
+            g.batch = np; g.sA = (long long)64 * ldw; g.sB = (long long)64 * ldw; g.sC = (long long)splits * 4096;
+            g.batch2 = splits; g.sA2 = Kc; g.sB2 = Kc; g.sC2 = 4096;
+            g.K_last = m - (splits - 1) * Kc;
+            gemm(g, st);
+            EigSmallParams e;
+            e.A = w.gram.p; e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; e.n = 64;
+            e.V = w.rot.p; e.ldv = 64; e.sV = 4096; e.relative = 1; e.offmax = w.offmax.p; e.batch = np;
+            e.max_sweeps = inner;
+            jacobi_eig_small(e, st);
+            GemmParams u;
+            u.A = cur; u.B = w.rot.p; u.C = nxt;
+            u.M = m; u.N = 64; u.K = 64; u.lda = ldw; u.ldb = 64; u.ldc = ldw;
+            u.batch = np; u.sA = (long long)64 * ldw; u.sB = 4096;
+            u.cblkmap = w.slotmap.p;
+            gemm(u, st);
+            std::swap(cur, nxt);
+        }
+        sweeps++;
+        double off = 0.0;
+        LRN_CUDA(cudaMemcpyAsync(&off, w.offmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        if (off <= tol) break;
+    }
+    colnorm_kernel<<<(unsigned)cdiv((long long)mp * nb * 32, 256), 256, 0, st>>>(cur, ldw, m, mp * nb, w.sv.p);
+    LRN_CHECK_LAUNCH();
+    rank_desc_batched_kernel<<<dim3((unsigned)cdiv(mp, 256), (unsigned)nb), 256, 0, st>>>(w.sv.p, mp, w.perm.p);
+    LRN_CHECK_LAUNCH();
+    svd_gather_batched_kernel<<<dim3((unsigned)cdiv(m, 256), (unsigned)m, (unsigned)nb), 256, 0, st>>>(cur, ldw, m, mp, w.perm.p, w.sv.p,
+                                                                                                     UD, ldu, sigma);
     LRN_CHECK_LAUNCH();
     return sweeps;
 }

@@ -56,6 +56,17 @@ struct SvdWork {
 int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, double* V, int ldv, double* sigma, SvdWork& w,
                      double tol, int max_sweeps, cudaStream_t st);
 
+// Batched variant for `nb` matrices of the SAME size m (multi-block SDPs): all blocks advance through the tournament in
+// lock step, so one Gram GEMM / one rotation kernel / one update GEMM per round serve every block.  No V accumulation.
+struct SvdBatchWork {
+    int m = 0, mp = 0, ldw = 0, nb = 0, splits = 1, Kc = 0;
+    DevBuf<double> buf0, buf1, gram, rot, offmax, sv;
+    DevBuf<int> slotmap, perm;
+    void ensure(int m_, int nb_);
+};
+int svd_block_jacobi_batched(const double* const* A, int lda, int m, int nb, double* const* UD, int ldu, double* const* sigma,
+                             SvdBatchWork& w, double tol, int max_sweeps, cudaStream_t st);
+
 struct LanczosWork {
     int m = 0, kmax = 0;
     DevBuf<double> Q;            // m x (kmax+1)
@@ -78,6 +89,12 @@ struct LanczosResult {
 // want: bit0 = smallest eigenvalue must converge, bit1 = largest nev_top must converge.
 LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_top, double* top_vals_host, double* top_vecs,
                               int ldv, double tol, LanczosWork& w, cudaStream_t st);
+
+// Batched smallest eigenvalue of small symmetric matrices (64 < m <= 512 is the intended range, any m >= 1 works): one CTA
+// per matrix reduces it to tridiagonal form by unblocked Householder reflections (matrix stays in L2, DESTROYED) and finds
+// the smallest eigenvalue by parallel multisection on Sturm counts.  Replaces `eigmin` for multi-block problems where a
+// Lanczos run per block would be launch-latency bound.  mats: device array of matrix pointers (full symmetric storage).
+void batched_lambda_min(double* const* mats, const int* ms, const int* lds, int count, double* out, cudaStream_t st);
 
 // Host-side symmetric tridiagonal eigen-solver (implicit QL). d[k] diag, e[k-1] offdiag. On return d = eigenvalues ascending;
 // if Z != nullptr it must be k x k (row-major identity on input not required) and receives the eigenvectors as columns

@@ -447,6 +447,42 @@ int32_t lrn_finalize(lrn_handle_t h) {
             h->blk[i].cholS.info_ext = h->blk_info.p + 2 * i + 1;
         }
         h->red.init(16 + 4 * std::max(1, h->nlmi));
+        {   // equal-sized blocks share a batched SVD
+            std::vector<std::pair<int, std::vector<int>>> bym;
+            for (int i = 0; i < h->nlmi; i++) {
+                bool found = false;
+                for (auto& g : bym) if (g.first == h->blk[i].m) { g.second.push_back(i); found = true; }
+                if (!found) bym.push_back({h->blk[i].m, {i}});
+            }
+            h->svd_group_of.assign(h->nlmi, -1);
+            for (auto& g : bym) {
+                if (g.second.size() < 2) continue;
+                auto G = std::make_unique<SvdGroup>();
+                G->m = g.first; G->blocks = g.second;
+                std::vector<const double*> a; std::vector<double*> ud, sg;
+                for (int i : g.second) {
+                    a.push_back(h->blk[i].T1.p()); ud.push_back(h->blk[i].T2.p()); sg.push_back(h->blk[i].D.p);
+                    h->svd_group_of[i] = (int)h->svd_groups.size();
+                }
+                G->A.upload(a, h->st); G->UD.upload(ud, h->st); G->sig.upload(sg, h->st);
+                h->svd_groups.push_back(std::move(G));
+            }
+        }
+        {   // small blocks get their two eigmin's per find_step from one batched launch
+            std::vector<double*> ptrs; std::vector<int> ms, lds;
+            for (int i = 0; i < h->nlmi; i++) {
+                Block& B = h->blk[i];
+                if (B.m > 64 && B.m <= 384) {
+                    h->eig_small.push_back(i);
+                    ptrs.push_back(B.T3.p()); ptrs.push_back(B.T1.p());
+                    ms.push_back(B.m); ms.push_back(B.m); lds.push_back(B.ld); lds.push_back(B.ld);
+                }
+            }
+            if (!ptrs.empty()) {
+                h->eig_ptrs.upload(ptrs, h->st); h->eig_ms.upload(ms, h->st); h->eig_lds.upload(lds, h->st);
+                h->eig_out.alloc(ptrs.size());
+            }
+        }
         bool rank1 = (h->opt.datarank == -1) && h->nlmi > 0;
         for (auto& B : h->blk) rank1 = rank1 && B.sp.has_B;
         if (h->opt.datarank == -1 && !rank1) h->opt.datarank = 0;      // src/Solvers.jl:435-444
@@ -557,11 +593,21 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             zero_strict_upper(B.LS.p(), m, ld, st);
             // CC = L_S' L_X                                                   (src/prepare_W.jl:39)
             gemm_tn(st, m, m, m, 1.0, B.LS.p(), ld, B.LX.p(), ld, 0.0, B.T1.p(), ld);
-            // U*D, D = svd(CC) without accumulating V                            (src/prepare_W.jl:42)
-            {
-                Phase ps(h, LRN_T_SVD);
-                h->stat_svd_sweeps = svd_block_jacobi(B.T1.p(), ld, m, B.T2.p(), ld, nullptr, 0, B.D.p, B.svd, svd_tol, 30, st);
+        }
+        // U*D, D = svd(CC) without accumulating V                                (src/prepare_W.jl:42)
+        {
+            Phase ps(h, LRN_T_SVD);
+            for (auto& G : h->svd_groups)
+                h->stat_svd_sweeps = svd_block_jacobi_batched(G->A.p, h->blk[G->blocks[0]].ld, G->m, (int)G->blocks.size(), G->UD.p,
+                                                              h->blk[G->blocks[0]].ld, G->sig.p, G->w, svd_tol, 30, st);
+            for (int i = 0; i < h->nlmi; i++) {
+                if (h->svd_group_of[i] >= 0) continue;
+                Block& B = h->blk[i];
+                h->stat_svd_sweeps = svd_block_jacobi(B.T1.p(), B.ld, B.m, B.T2.p(), B.ld, nullptr, 0, B.D.p, B.svd, svd_tol, 30, st);
             }
+        }
+        for (auto& B : h->blk) {
+            const int m = B.m, ld = B.ld;
             vec_op(st, m, VEC_RSQRT, B.dm12.p, B.D.p, nullptr);
             vec_op(st, m, VEC_POW_M32, B.dm32.p, B.D.p, nullptr);
             // G = L_X V D^{-1/2} = L_S^{-T} (U D) D^{-1/2}   (CC V = U D with CC = L_S' L_X)   (src/prepare_W.jl:60)
@@ -783,12 +829,29 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
             gemm_nt(st, m, m, m, 1.0, B.dX.p(), ld, B.Gi.p(), ld, 0.0, B.T1.p(), ld);
             gemm_nn(st, m, m, m, 1.0, B.Gi.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
             mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
-            alpha[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
+            const bool batched = (m > 64 && m <= 384);
+            if (!batched) alpha[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
             // delSb = G' delS G                                                (:263,:281-285)
             gemm_nn(st, m, m, m, 1.0, B.dS.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
             gemm_tn(st, m, m, m, 1.0, B.G.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
-            mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
-            beta[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
+            if (batched) {
+                mat_scaled_sym(st, m, B.T1.p(), ld, B.T2.p(), ld, B.DDsi.p);      // X part stays in T3, S part in T1
+            } else {
+                mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
+                beta[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
+            }
+        }
+        if (!h->eig_small.empty()) {
+            Phase pe(h, LRN_T_EIGMIN);
+            const int cnt = 2 * (int)h->eig_small.size();
+            batched_lambda_min(h->eig_ptrs.p, h->eig_ms.p, h->eig_lds.p, cnt, h->eig_out.p, st);
+            std::vector<double> lam(cnt);
+            LRN_CUDA(cudaMemcpyAsync(lam.data(), h->eig_out.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            LRN_CUDA(cudaStreamSynchronize(st));
+            for (size_t t = 0; t < h->eig_small.size(); t++) {
+                alpha[h->eig_small[t]] = steplen(lam[2 * t], tau);
+                beta[h->eig_small[t]] = steplen(lam[2 * t + 1], tau);
+            }
         }
         *alpha_lin = 1.0;
         *beta_lin = 1.0;

@@ -36,6 +36,14 @@ struct Block {
     double tau = 0.0;
 };
 
+struct SvdGroup {                       // PSD blocks of equal size share one batched block-Jacobi SVD
+    int m = 0;
+    std::vector<int> blocks;
+    SvdBatchWork w;
+    DevBuf<const double*> A;
+    DevBuf<double*> UD, sig;
+};
+
 struct PhaseEvt {
     cudaEvent_t a, b;
     int phase;
@@ -59,6 +67,13 @@ struct lrn_solver {
     lrn::CholWork cholH;
     bool have_factor = false;
     lrn::DevBuf<int> blk_info;         // 2 per block (chol X, chol S)
+    // batched lambda_min of the small blocks (m <= EIG_BATCH_MAXM): matrices T3_i (X part) and T1_i (S part)
+    std::vector<std::unique_ptr<lrn::SvdGroup>> svd_groups;
+    std::vector<int> svd_group_of;     // per block: group index or -1
+    std::vector<int> eig_small;        // block indices handled by the batched kernel
+    lrn::DevBuf<double*> eig_ptrs;
+    lrn::DevBuf<int> eig_ms, eig_lds;
+    lrn::DevBuf<double> eig_out;
     lrn::Reducer red;
     lrn::LanczosWork lan;
     cudaStream_t st = nullptr;

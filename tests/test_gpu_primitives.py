@@ -20,6 +20,7 @@ def L(pkg):
     lib.lrn_dbg_svd.argtypes = [i32, pd, pd, pd, pd, dbl, pi, pd]
     lib.lrn_dbg_lanczos.argtypes = [i32, pd, i32, dbl, pd, pd, pd, pd, pi, pi]
     lib.lrn_dbg_peak.argtypes = [i32, pd]
+    lib.lrn_dbg_batched_lambda_min.argtypes = [i32, i32, pd, pd]
     return lib
 
 
@@ -158,3 +159,21 @@ def test_lanczos_extremes(L, m):
     ref = np.sort(lam)[-2:]
     assert np.max(np.abs(tv - ref)) <= 1e-9 * np.abs(lam).max()
     assert np.linalg.norm(T @ tvec - tvec * tv[None, :]) <= 1e-7 * np.abs(lam).max()
+
+
+@pytest.mark.parametrize("m,count", [(1, 3), (2, 2), (3, 4), (65, 5), (200, 7), (384, 3)])
+def test_batched_lambda_min(L, m, count):
+    """one CTA per matrix: Householder tridiagonalisation + Sturm multisection vs LAPACK eigvalsh"""
+    rng = np.random.default_rng(m + count)
+    mats = np.zeros((count, m, m))
+    for z in range(count):
+        A = rng.standard_normal((m, m))
+        mats[z] = (A + A.T) / 2 - (z % 2) * 3.0 * np.eye(m)
+    if count > 2 and m > 2:
+        mats[2] = np.diag(np.linspace(-2.0, 5.0, m))            # already diagonal (all reflections skipped)
+    flat = np.ascontiguousarray(np.stack([np.asfortranarray(a).ravel(order="F") for a in mats]))
+    out = np.zeros(count)
+    assert L.lrn_dbg_batched_lambda_min(count, m, dp(flat), dp(out)) == 0
+    ref = np.array([np.linalg.eigvalsh(a)[0] for a in mats])
+    scale = np.array([max(1.0, np.abs(np.linalg.eigvalsh(a)).max()) for a in mats])
+    assert np.max(np.abs(out - ref) / scale) <= 1e-13
