@@ -3,6 +3,7 @@
 // DMMA SYRK-shaped GEMM with K = panel width (64..512, recursion keeps the bulk of the flops in large-K updates).
 #include "chol.cuh"
 #include "gemm.cuh"
+#include <cooperative_groups.h>
 
 namespace lrn {
 namespace {
@@ -14,16 +15,68 @@ constexpr size_t POTRF_SMEM = (2 * DB * SLD + DB + 2 + 4 * DB) * sizeof(double);
 // One CTA factors a 64x64 diagonal block held in REGISTERS (each of the 256 threads owns a cyclic 4x4 sub-tile: rows
 // ti+16a, columns tj+16b), two barriers per column; the inverse of the factor is then built row by row in shared memory
 // (4 partial dot products per entry).  ~15 us instead of ~100 us for the previous shared-memory version.
-__global__ void __launch_bounds__(256)
-    potrf_diag_kernel(double* __restrict__ A, int lda, int nb, double* __restrict__ dinv, int* __restrict__ info, int base) {
-    extern __shared__ double sm[];
-    double* sL = sm;                      // factor (lower), later read by the inversion   [DB][SLD]
-    double* sX = sm + DB * SLD;           // inverse                                        [DB][SLD]
-    double* colbuf = sX + DB * SLD;       // [DB]
-    double* dbuf = colbuf + DB;           // [2]
-    double (*part)[DB] = reinterpret_cast<double (*)[DB]>(dbuf + 2);   // [4][DB]
+// 16 consecutive columns j = 16*JA + jm of the register-resident 64x64 factorisation.  JA is a compile-time constant so that
+// every "is this my row / column block" test folds away and the triangular structure skips whole 16x16 register sub-blocks.
+template <int JA>
+__device__ __forceinline__ void potrf64_steps(double (&r)[4][4], double (&z)[4][4], double* colbuf, double* rowbuf, int ti, int tj,
+                                              int nb, int* __restrict__ info, int base) {
+    for (int jm = 0; jm < 16; jm++) {
+        const int j = JA * 16 + jm;
+        double* cb = colbuf + (j & 1) * DB;
+        double* rb = rowbuf + (j & 1) * DB;
+        if (tj == jm) {                                   // owners of column j publish the raw column a(j:,j)
+#pragma unroll
+            for (int a = JA; a < 4; a++) cb[ti + 16 * a] = r[a][JA];
+        }
+        if (ti == jm) {                                   // owners of row j publish Z(j,0:j)
+#pragma unroll
+            for (int b = 0; b <= JA; b++) rb[tj + 16 * b] = z[JA][b];
+        }
+        __syncthreads();
+        double d = cb[j];
+        if (!(d > 0.0)) {                                  // also catches NaN; every thread substitutes the same value
+            if (threadIdx.x == 0 && j < nb && *info == 0) *info = base + j + 1;
+            d = 1.0;
+        }
+        const double rs = rsqrt(d), rd = rs * rs;           // 1/l_jj and 1/d
+        double ck[4], rk[4];
+#pragma unroll
+        for (int b = JA; b < 4; b++) ck[b] = (b > JA || tj > jm) ? cb[tj + 16 * b] : 0.0;
+#pragma unroll
+        for (int b = 0; b <= JA; b++) rk[b] = rb[tj + 16 * b];
+#pragma unroll
+        for (int a = JA; a < 4; a++) {
+            const double ci = cb[ti + 16 * a];
+            const double li = (a > JA || ti > jm) ? ci * rd : 0.0;
+#pragma unroll
+            for (int b = JA; b < 4; b++) r[a][b] = fma(-li, ck[b], r[a][b]);       // trailing matrix
+#pragma unroll
+            for (int b = 0; b <= JA; b++) z[a][b] = fma(-li, rk[b], z[a][b]);      // Z(i,:) -= (a_ij / d) Z(j,:)
+        }
+        if (ti == jm) {                                   // E(j,:) = Z(j,:) / l_jj
+#pragma unroll
+            for (int b = 0; b <= JA; b++) z[JA][b] *= rs;
+        }
+        if (tj == jm) {                                   // column j is final: l_ij = a_ij / l_jj, l_jj = d / l_jj
+#pragma unroll
+            for (int a = JA; a < 4; a++) {
+                if (a > JA || ti > jm) r[a][JA] = cb[ti + 16 * a] * rs;
+                else if (ti == jm) r[a][JA] = d * rs;
+            }
+        }
+    }
+}
+
+// Factor a 64x64 block held in REGISTERS (each of the 256 threads owns the cyclic 4x4 sub-tile rows ti+16a, columns tj+16b)
+// and build the inverse of the factor in the same sweep: with Z = I,  step j:  E(j,:) = Z(j,:)/l_jj ;  Z(i,:) -= l_ij E(j,:)
+// for i > j (forward substitution on the identity, right-looking) -- one block barrier and one rsqrt per column, no
+// separate inversion phase.
+__device__ __forceinline__ void potrf64_block(double* __restrict__ A, int lda, int nb, double* __restrict__ dinv,
+                                              int* __restrict__ info, int base, double* sm) {
+    double* colbuf = sm;                  // [2][DB]  raw column j of the trailing matrix   (double buffered)
+    double* rowbuf = sm + 2 * DB;         // [2][DB]  row j of Z
     const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
-    double r[4][4];
+    double r[4][4], z[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -33,87 +86,196 @@ __global__ void __launch_bounds__(256)
             if (i < nb && k < nb) v = (i >= k) ? A[(size_t)k * lda + i] : A[(size_t)i * lda + k];   // symmetric fill from the lower part
             else if (i == k) v = 1.0;                                                            // identity padding
             r[a][b] = v;
+            z[a][b] = (i == k) ? 1.0 : 0.0;
         }
-    for (int j = 0; j < DB; j++) {
-        const int ja = j >> 4, jm = j & 15;
-        if (ti == jm && tj == jm) {                       // owner of the diagonal entry
-            double d = 0.0;
+    potrf64_steps<0>(r, z, colbuf, rowbuf, ti, tj, nb, info, base);
+    potrf64_steps<1>(r, z, colbuf, rowbuf, ti, tj, nb, info, base);
+    potrf64_steps<2>(r, z, colbuf, rowbuf, ti, tj, nb, info, base);
+    potrf64_steps<3>(r, z, colbuf, rowbuf, ti, tj, nb, info, base);
 #pragma unroll
-            for (int a = 0; a < 4; a++) if (a == ja) d = r[a][a];
-            if (!(d > 0.0)) {
-                if (j < nb && *info == 0) *info = base + j + 1;
-                d = 1.0;
-            }
-            dbuf[j & 1] = sqrt(d);
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int i = ti + 16 * a, k = tj + 16 * b;
+            if (i < nb && k < nb && i >= k) A[(size_t)k * lda + i] = r[a][b];
+            dinv[(size_t)k * DB + i] = (i < nb && k < nb && i >= k) ? z[a][b] : 0.0;
         }
-        __syncthreads();
-        const double djj = dbuf[j & 1];
-        if (tj == jm) {                                   // owners of column j publish l(:,j)
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int i = ti + 16 * a;
-                double v = 0.0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) if (b == ja) v = r[a][b];
-                v = (i > j) ? v / djj : (i == j ? djj : 0.0);
-                colbuf[i] = v;
-                sL[i * SLD + j] = v;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int i = ti + 16 * a;
-            const double li = colbuf[i];
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int k = tj + 16 * b;
-                if (i > j && k > j) r[a][b] -= li * colbuf[k];
-            }
-        }
-        // colbuf of step j is re-written only after the next barrier pair; dbuf is double buffered
+}
+
+__global__ void __launch_bounds__(256)
+    potrf_diag_kernel(double* __restrict__ A, int lda, int nb, double* __restrict__ dinv, int* __restrict__ info, int base) {
+    extern __shared__ double sm[];
+    potrf64_block(A, lda, nb, dinv, info, base, sm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cooperative small-matrix Cholesky (64 < n <= 512): ONE launch factors the whole block, produces the inverted 64x64
+// diagonal blocks and (optionally) the full inverse of the factor.  Replaces ~60 dependent tiny launches per 512-block
+// (the latency chain that bounded the factorisation of mid-size Schur matrices and of the PSD blocks).
+// Grid-wide barriers (cooperative launch) separate: diagonal block factorisation (CTA 0) | row-block solves | trailing tiles.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TLD = DB + 1;     // padded k-stride of the shared-memory tiles
+
+// s[k*TLD + i] = G[i + k*ld]  (i < rows, k < cols; zero elsewhere)
+__device__ __forceinline__ void tile_load(double* s, const double* __restrict__ G, int ld, int rows, int cols) {
+    for (int idx = threadIdx.x; idx < DB * DB; idx += 256) {
+        const int i = idx & 63, k = idx >> 6;
+        s[k * TLD + i] = (i < rows && k < cols) ? G[(size_t)k * ld + i] : 0.0;
     }
-    __syncthreads();
-    // inverse, row by row: x(i,c) = -( sum_{k=c}^{i-1} L(i,k) x(k,c) ) / L(i,i),  x(i,i) = 1 / L(i,i)
-    const int c = tid & 63, pr = tid >> 6;
-    for (int i = 0; i < DB; i++) {
-        double acc = 0.0;
-        for (int k = c + pr; k < i; k += 4) acc += sL[i * SLD + k] * sX[k * SLD + c];
-        part[pr][c] = acc;
-        __syncthreads();
-        if (pr == 0) {
-            double v = 0.0;
-            const double lii = sL[i * SLD + i];
-            if (c == i) v = 1.0 / lii;
-            else if (c < i) v = -(part[0][c] + part[1][c] + part[2][c] + part[3][c]) / lii;
-            sX[i * SLD + c] = v;
-        }
-        __syncthreads();
+}
+// s[k*TLD + j] = G[k + j*ld]  (k < rows, j < cols): the transposed placement
+__device__ __forceinline__ void tile_load_t(double* s, const double* __restrict__ G, int ld, int rows, int cols) {
+    for (int idx = threadIdx.x; idx < DB * DB; idx += 256) {
+        const int k = idx & 63, j = idx >> 6;
+        s[k * TLD + j] = (k < rows && j < cols) ? G[(size_t)j * ld + k] : 0.0;
     }
-    for (int idx = tid; idx < DB * DB; idx += 256) {
-        int i = idx % DB, j = idx / DB;
-        if (i < nb && j < nb && i >= j) A[(size_t)j * lda + i] = sL[i * SLD + j];
-        dinv[(size_t)j * DB + i] = (i < nb && j < nb) ? sX[i * SLD + j] : 0.0;
+}
+// acc[a][b] += sum_k As[k][ti+16a] * Bs[k][tj+16b]
+__device__ __forceinline__ void tile_prod(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][4]) {
+    const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+#pragma unroll 8
+    for (int k = 0; k < DB; k++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { a[t] = As[k * TLD + ti + 16 * t]; b[t] = Bs[k * TLD + tj + 16 * t]; }
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
     }
 }
 
-int pick_nb(int n) {
-    if (n > 8192) return 512;
-    if (n > 2048) return 256;
-    if (n > 512) return 128;
-    return 64;
+__global__ void __launch_bounds__(256)
+    potrf_coop_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ dinv, double* __restrict__ X, int ldx,
+                      int* __restrict__ info, int base) {
+    extern __shared__ double sm[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    double* As = sm;
+    double* Bs = sm + DB * TLD;
+    const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    const int nb = (n + DB - 1) / DB;
+    for (int j = 0; j < nb; j++) {
+        const int j0 = j * DB, jb = min(DB, n - j0);
+        if (c == 0) potrf64_block(A + (size_t)j0 * lda + j0, lda, jb, dinv + (size_t)j * DB * DB, info, base + j0, sm);
+        __threadfence();
+        grid.sync();
+        for (int i = j + 1 + c; i < nb; i += G) {                      // P_i <- P_i * inv(L_jj)^T
+            const int i0 = i * DB, ib = min(DB, n - i0);
+            __syncthreads();
+            tile_load(As, A + (size_t)j0 * lda + i0, lda, ib, jb);
+            tile_load(Bs, dinv + (size_t)j * DB * DB, DB, DB, DB);     // Bs[k][cc] = dinv[cc + k*64] = inv(L_jj)[cc][k]
+            __syncthreads();
+            double acc[4][4] = {};
+            tile_prod(As, Bs, acc);
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const int a = ti + 16 * x, b = tj + 16 * y;
+                    if (a < ib && b < jb) A[(size_t)(j0 + b) * lda + i0 + a] = acc[x][y];
+                }
+        }
+        __threadfence();
+        grid.sync();
+        const int t = nb - 1 - j, ntile = t * (t + 1) / 2;
+        for (int tile = c; tile < ntile; tile += G) {                  // A_rc -= P_r P_c^T   (j < cc <= r)
+            int rr = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+            while ((rr + 1) * (rr + 2) / 2 <= tile) rr++;
+            while (rr * (rr + 1) / 2 > tile) rr--;
+            const int cc = tile - rr * (rr + 1) / 2;
+            const int r0 = (j + 1 + rr) * DB, c0 = (j + 1 + cc) * DB, rb = min(DB, n - r0), cb = min(DB, n - c0);
+            __syncthreads();
+            tile_load(As, A + (size_t)j0 * lda + r0, lda, rb, jb);
+            tile_load(Bs, A + (size_t)j0 * lda + c0, lda, cb, jb);
+            __syncthreads();
+            double acc[4][4] = {};
+            tile_prod(As, Bs, acc);
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const int a = ti + 16 * x, b = tj + 16 * y;
+                    if (a < rb && b < cb) A[(size_t)(c0 + b) * lda + r0 + a] -= acc[x][y];
+                }
+        }
+        __threadfence();
+        grid.sync();
+    }
+    if (!X) return;
+    // full inverse of the factor: X_ii = inv(L_ii);  X_ic = -inv(L_ii) * sum_{k=c}^{i-1} L_ik X_kc   (block row after block row)
+    for (int i = c; i < nb; i += G) {
+        const int i0 = i * DB, ib = min(DB, n - i0);
+        for (int idx = tid; idx < DB * DB; idx += 256) {
+            const int a = idx & 63, b = idx >> 6;
+            if (a < ib && b < ib) X[(size_t)(i0 + b) * ldx + i0 + a] = dinv[(size_t)i * DB * DB + (size_t)b * DB + a];
+        }
+    }
+    __threadfence();
+    grid.sync();
+    for (int i = 1; i < nb; i++) {
+        const int i0 = i * DB, ib = min(DB, n - i0);
+        for (int cc = c; cc < i; cc += G) {
+            const int c0 = cc * DB;
+            double acc[4][4] = {};
+            for (int k = cc; k < i; k++) {
+                const int k0 = k * DB;
+                __syncthreads();
+                tile_load(As, A + (size_t)k0 * lda + i0, lda, ib, DB);          // As[t][a] = L_ik[a][t]
+                tile_load_t(Bs, X + (size_t)c0 * ldx + k0, ldx, DB, DB);        // Bs[t][b] = X_kc[t][b]
+                __syncthreads();
+                tile_prod(As, Bs, acc);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) Bs[(ti + 16 * x) * TLD + tj + 16 * y] = acc[x][y];   // Bs[t][b] = acc[t][b]
+            tile_load(As, dinv + (size_t)i * DB * DB, DB, DB, DB);              // As[t][a] = inv(L_ii)[a][t]
+            __syncthreads();
+            double acc2[4][4] = {};
+            tile_prod(As, Bs, acc2);
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const int a = ti + 16 * x, b = tj + 16 * y;
+                    if (a < ib) X[(size_t)(c0 + b) * ldx + i0 + a] = -acc2[x][y];
+                }
+        }
+        __threadfence();
+        grid.sync();
+    }
 }
 
-// P (rows x kb, below a factored kb x kb diagonal block Akk) <- P * inv(L_kk)^T, 64 columns at a time
-void panel_trsm(double* P, int rows, int kb, const double* Akk, const double* dk, int lda, cudaStream_t st) {
-    for (int j = 0; j < kb; j += DB) {
-        const int jb = (kb - j < DB) ? (kb - j) : DB;
-        double* Pj = P + (size_t)j * lda;
-        // Pj -= P[:,0:j] * L[k+j : k+j+jb, k : k+j]^T
-        if (j > 0) gemm_nt(st, rows, jb, j, -1.0, P, lda, Akk + j, lda, 1.0, Pj, lda);
-        // Pj <- Pj * inv(L_jj)^T   (in place: every CTA owns its rows and a single N tile)
-        gemm_nt(st, rows, jb, jb, 1.0, Pj, lda, dk + (size_t)(j / DB) * DB * DB, DB, 0.0, Pj, lda);
+constexpr int COOP_MAXN = 512;
+
+int pick_nb(int n) { return n > 8192 ? 512 : 256; }
+
+void potrf_launch_config() {
+    static bool configured = false;
+    if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+        LRN_CUDA(cudaFuncSetAttribute(potrf_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+        configured = true;
     }
+}
+
+// factor a block of side n <= 512 with one launch; X (optional, n x n, ldx) receives the full inverse of the factor
+void potrf_small(double* A, int lda, int n, double* dinv, double* X, int ldx, int* info, int base, cudaStream_t st) {
+    potrf_launch_config();
+    if (n <= DB && !X) {
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(A, lda, n, dinv, info, base);
+        LRN_CHECK_LAUNCH();
+        return;
+    }
+    LRN_REQUIRE(n <= COOP_MAXN, "potrf_small handles n <= 512");
+    if (X) LRN_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * n * sizeof(double), st));
+    const int nb = (int)cdiv(n, DB);
+    int G = nb * (nb - 1) / 2;
+    G = G < 1 ? 1 : (G > 28 ? 28 : G);
+    void* args[] = {&A, &lda, &n, &dinv, &X, &ldx, &info, &base};
+    LRN_CUDA(cudaLaunchCooperativeKernel((void*)potrf_coop_kernel, dim3(G), dim3(256), args, POTRF_SMEM, st));
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 __global__ void k_copy2d(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
@@ -127,47 +289,51 @@ void copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols
     LRN_CHECK_LAUNCH();
 }
 
-// X = inv(L_kk) (kb x kb lower, leading dimension ldx) from the factor and its inverted 64x64 diagonal blocks:
-// block row i:  X[i, 0:i) = -inv(L_ii) * ( L[i, 0:i) * X[0:i, 0:i) ),  X[i,i] = inv(L_ii).   2 small GEMMs per block row.
-void trtri_blocked(const double* Lkk, int kb, int lda, const double* dk, double* X, int ldx, double* T, cudaStream_t st) {
-    LRN_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * kb * sizeof(double), st));
-    const int nb = (int)cdiv(kb, DB);
-    for (int i = 0; i < nb; i++) {
-        const int i0 = i * DB, ib = (kb - i0 < DB) ? (kb - i0) : DB;
-        const double* di = dk + (size_t)i * DB * DB;
-        copy2d(di, DB, X + (size_t)i0 * ldx + i0, ldx, ib, ib, st);
-        if (i > 0) {
-            gemm_nn(st, ib, i0, i0, 1.0, Lkk + i0, lda, X, ldx, 0.0, T, DB);
-            gemm_nn(st, ib, i0, ib, -1.0, di, DB, T, DB, 0.0, X + i0, ldx);
-        }
+// P (rows x kb, below a factored kb x kb diagonal block Akk) <- P * inv(L_kk)^T, 64 columns at a time (small panels)
+void panel_trsm(double* P, int rows, int kb, const double* Akk, const double* dk, int lda, cudaStream_t st) {
+    for (int j = 0; j < kb; j += DB) {
+        const int jb = (kb - j < DB) ? (kb - j) : DB;
+        double* Pj = P + (size_t)j * lda;
+        if (j > 0) gemm_nt(st, rows, jb, j, -1.0, P, lda, Akk + j, lda, 1.0, Pj, lda);
+        gemm_nt(st, rows, jb, jb, 1.0, Pj, lda, dk + (size_t)(j / DB) * DB * DB, DB, 0.0, Pj, lda);
     }
 }
 
-// rows below a factored kb x kb diagonal block: P <- P * inv(L_kk)^T as ONE large GEMM through the explicit inverse
-// (out of place into work.pout or the caller's buffer, then copied back)
-void panel_trsm_inv(double* P, int rows, int kb, const double* Akk, const double* dk, int lda, CholWork& work, double* Pout,
-                    int ldp, cudaStream_t st) {
+// Factor the kb x kb diagonal block at the top of a panel and solve the `rows` rows below it:
+//   large panels: explicit inverse X (from the cooperative kernel) and ONE DMMA GEMM  P <- P X^T (out of place, copied back)
+//   small panels: 64-column TRSM through the inverted diagonal blocks
+// If Pout != null the solved rows are left in Pout (leading dimension ldp) as well.
+void factor_panel(double* Akk, int kb, int rows, int lda, double* dk, int* info, int base, CholWork& work, double* Pout, int ldp,
+                  cudaStream_t st) {
+    const bool useinv = (kb >= 128 && rows >= 512);
+    double* X = nullptr;
     const int ldx = pad_ld(kb);
-    const size_t need = (size_t)ldx * kb + (size_t)DB * kb;
-    if (work.xinv.n < need) work.xinv.alloc(need);
-    double* X = work.xinv.p;
-    double* T = X + (size_t)ldx * kb;
-    trtri_blocked(Akk, kb, lda, dk, X, ldx, T, st);
-    double* out = Pout;
-    int ldo = ldp;
-    if (!out) {
-        ldo = pad_ld(rows);
-        if (work.pout.n < (size_t)ldo * kb) work.pout.alloc((size_t)ldo * kb);
-        out = work.pout.p;
+    if (useinv) {
+        if (work.xinv.n < (size_t)ldx * kb) work.xinv.alloc((size_t)ldx * kb);
+        X = work.xinv.p;
     }
-    gemm_nt(st, rows, kb, kb, 1.0, P, lda, X, ldx, 0.0, out, ldo);
-    copy2d(out, ldo, P, lda, rows, kb, st);
+    potrf_small(Akk, lda, kb, dk, X, ldx, info, base, st);
+    if (rows <= 0) return;
+    double* P = Akk + kb;
+    if (useinv) {
+        double* out = Pout;
+        int ldo = ldp;
+        if (!out) {
+            ldo = pad_ld(rows);
+            if (work.pout.n < (size_t)ldo * kb) work.pout.alloc((size_t)ldo * kb);
+            out = work.pout.p;
+        }
+        gemm_nt(st, rows, kb, kb, 1.0, P, lda, X, ldx, 0.0, out, ldo);
+        copy2d(out, ldo, P, lda, rows, kb, st);
+    } else {
+        panel_trsm(P, rows, kb, Akk, dk, lda, st);
+        if (Pout) copy2d(P, lda, Pout, ldp, rows, kb, st);
+    }
 }
 
 void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, CholWork& work, cudaStream_t st) {
-    if (n <= DB) {
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(A, lda, n, dinv, info, base);
-        LRN_CHECK_LAUNCH();
+    if (n <= COOP_MAXN) {
+        potrf_small(A, lda, n, dinv, nullptr, 0, info, base, st);
         return;
     }
     const int NB = pick_nb(n);
@@ -175,12 +341,10 @@ void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, Chol
         const int kb = (n - k < NB) ? (n - k) : NB;
         double* Akk = A + (size_t)k * lda + k;
         double* dk = dinv + (size_t)(k / DB) * DB * DB;
-        chol_rec(Akk, kb, lda, dk, info, base + k, work, st);
         const int rows = n - k - kb;
+        factor_panel(Akk, kb, rows, lda, dk, info, base + k, work, nullptr, 0, st);
         if (rows <= 0) break;
         double* P = A + (size_t)k * lda + (k + kb);          // rows x kb panel below the diagonal block
-        if (kb >= 128 && rows >= 1024) panel_trsm_inv(P, rows, kb, Akk, dk, lda, work, nullptr, 0, st);
-        else panel_trsm(P, rows, kb, Akk, dk, lda, st);
         // trailing update, lower triangle only
         GemmParams p;
         p.A = P; p.B = P; p.C = A + (size_t)(k + kb) * lda + (k + kb);
@@ -248,32 +412,62 @@ __global__ void zero_upper_kernel(double* A, int n, int lda) {
 
 void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
                     int ldp, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
-        configured = true;
-    }
-    chol_rec(Apanel, w, lda, dinv, info, base, work, st);
-    if (rows > w) {
-        if (w >= 128 && rows - w >= 1024) panel_trsm_inv(Apanel + w, rows - w, w, Apanel, dinv, lda, work, Pout ? Pout + w : nullptr, ldp, st);
-        else {
-            panel_trsm(Apanel + w, rows - w, w, Apanel, dinv, lda, st);
-            if (Pout) copy2d(Apanel + w, lda, Pout + w, ldp, rows - w, w, st);
+    factor_panel(Apanel, w, rows - w, lda, dinv, info, base, work, Pout ? Pout + w : nullptr, ldp, st);
+    if (Pout) copy2d(Apanel, lda, Pout, ldp, w, w, st);
+}
+
+void ensure_aux(CholWork& work) {
+    if (work.aux) return;
+    int lo = 0, hi = 0;
+    LRN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LRN_CUDA(cudaStreamCreateWithPriority(&work.aux, cudaStreamNonBlocking, hi));
+    for (auto& e : work.ev) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+// Right-looking factorisation with one-step look-ahead on two streams: the latency-bound panel work (cooperative diagonal
+// block kernel + panel solve) of panel p+1 runs on a high-priority side stream while `st` still applies the bulk of the
+// trailing update of panel p.
+void chol_lookahead(double* A, int n, int lda, CholWork& work, cudaStream_t st) {
+    ensure_aux(work);
+    cudaStream_t sp = work.aux;
+    cudaEvent_t evStart = work.ev[0], evU = work.ev[1], evF[2] = {work.ev[2], work.ev[3]};
+    int* info = work.info_ptr();
+    const int NB = pick_nb(n), npan = (int)cdiv(n, NB);
+    LRN_CUDA(cudaEventRecord(evStart, st));
+    LRN_CUDA(cudaStreamWaitEvent(sp, evStart, 0));
+    for (int p = 0; p < npan; p++) {
+        const int c0 = p * NB, w = (n - c0 < NB) ? (n - c0) : NB, rows = n - c0;
+        double* Ap = A + (size_t)c0 * lda + c0;
+        double* dk = work.dinv.p + (size_t)(c0 / DB) * DB * DB;
+        if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));           // panel p has received the update of panel p-1
+        factor_panel(Ap, w, rows - w, lda, dk, info, c0, work, nullptr, 0, sp);
+        LRN_CUDA(cudaEventRecord(evF[p & 1], sp));
+        LRN_CUDA(cudaStreamWaitEvent(st, evF[p & 1], 0));
+        const int q0 = c0 + w;
+        if (q0 >= n) break;
+        const int wq = (n - q0 < NB) ? (n - q0) : NB;
+        const double* P = Ap + w;                                           // rows below the diagonal block, lda
+        // next panel column first ...
+        gemm_nt(st, n - q0, wq, w, -1.0, P, lda, P, lda, 1.0, A + (size_t)q0 * lda + q0, lda);
+        LRN_CUDA(cudaEventRecord(evU, st));
+        // ... then the rest of the trailing matrix (lower triangle)
+        const int q1 = q0 + wq;
+        if (q1 < n) {
+            GemmParams g;
+            g.A = P + wq; g.B = P + wq; g.C = A + (size_t)q1 * lda + q1;
+            g.M = n - q1; g.N = n - q1; g.K = w; g.lda = lda; g.ldb = lda; g.ldc = lda;
+            g.transB = true; g.alpha = -1.0; g.beta = 1.0; g.lower = 1;
+            gemm(g, st);
         }
     }
-    if (Pout) copy2d(Apanel, lda, Pout, ldp, w, w, st);
 }
 
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st) {
     work.ensure(n);
-    static bool configured = false;
-    if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
-        configured = true;
-    }
     LRN_CUDA(cudaMemsetAsync(work.info_ptr(), 0, sizeof(int), st));
     if (n <= 0) return;
-    chol_rec(A, n, lda, work.dinv.p, work.info_ptr(), 0, work, st);
+    if (n >= 1024) chol_lookahead(A, n, lda, work, st);
+    else chol_rec(A, n, lda, work.dinv.p, work.info_ptr(), 0, work, st);
 }
 
 void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {

@@ -36,6 +36,9 @@ void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st);
 void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
                     int ldp, cudaStream_t st);
 
+// creates the high-priority side stream and the events of `work` on first use
+void ensure_aux(CholWork& work);
+
 // x <- L^{-1} x (which=1), x <- L^{-T} x (which=2), both (which=3). `tmp` has n doubles. Uses work.dinv of the same factor.
 void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st);
 

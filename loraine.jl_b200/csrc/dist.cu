@@ -52,12 +52,7 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
     const size_t ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
     const size_t bufsz = (size_t)ldp * pw + ndmax + 8;
     if (panelbuf.n < 2 * bufsz) panelbuf.alloc(2 * bufsz);
-    if (!work.aux) {
-        int lo = 0, hi = 0;
-        LRN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        LRN_CUDA(cudaStreamCreateWithPriority(&work.aux, cudaStreamNonBlocking, hi));
-        for (auto& e : work.ev) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    ensure_aux(work);
     cudaStream_t sp = work.aux;                     // panel stream: factor panel p+1 and broadcast it while `st` still
     cudaEvent_t evStart = work.ev[0], evU = work.ev[1];   // applies the trailing updates of panel p (one-step look-ahead)
     cudaEvent_t evB[2] = {work.ev[2], work.ev[3]}, evE[2] = {work.ev[4], work.ev[5]};

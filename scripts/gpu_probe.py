@@ -65,11 +65,11 @@ for (M, N, K, ta, tb) in sizes:
     print("gemm", M, N, K, ta, tb, "%.3f ms %.2f TF/s" % (ms.value, tf), flush=True)
 out["gemm"] = res
 ch = []
-for n in (1000, 5000, 10000):
+for n in (64, 128, 256, 512, 1000, 2000, 5000, 10000):
     Gm = rng.standard_normal((n, n))
     A = np.asfortranarray(Gm @ Gm.T / n + np.eye(n))
     info, ms = C.c_int32(), C.c_double()
-    L.lrn_dbg_cholesky(n, dp(A), None, 0, C.byref(info), 2, C.byref(ms))
+    L.lrn_dbg_cholesky(n, dp(A), None, 0, C.byref(info), 5, C.byref(ms))
     tf = n ** 3 / 3 / (ms.value * 1e-3) / 1e12
     ch.append(dict(n=n, ms=ms.value, tflops=tf, info=info.value))
     print("chol", n, "%.3f ms %.2f TF/s info %d" % (ms.value, tf, info.value), flush=True)
