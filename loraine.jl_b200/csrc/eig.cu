@@ -71,12 +71,17 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
         if (tid == 0) rotated = 0;
         __syncthreads();
         for (int r = 0; r < n2 - 1; r++) {
-            if (tid < h) {
+            // every warp owns 4 of the (at most 32) disjoint pairs of this step: lanes 0..3 compute the rotations of the
+            // warp's own pairs (they only read rows p,q that no other warp writes in the row phase), no block barrier needed
+            const int lane = tid & 31, wk0 = (tid >> 5) * 4;
+            double c_l = 1.0, s_l = 0.0;
+            int p_l = 0, q_l = 0;
+            if (lane < 4 && wk0 + lane < h) {
+                const int k = wk0 + lane;
                 int p, q;
-                if (tid == 0) { p = n2 - 1; q = r; }
-                else { p = (r + tid) % (n2 - 1); q = (r - tid + (n2 - 1)) % (n2 - 1); }
+                if (k == 0) { p = n2 - 1; q = r; }
+                else { p = (r + k) % (n2 - 1); q = (r - k + (n2 - 1)) % (n2 - 1); }
                 if (p > q) { int t = p; p = q; q = t; }
-                double c = 1.0, s = 0.0;
                 if (q < n) {
                     double apq = a[p * ELD + q], app = a[p * ELD + p], aqq = a[q * ELD + q];
                     double thr = fmax(rel_tol * sqrt(fabs(app * aqq)), abs_tol);
@@ -85,23 +90,20 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
                         double t;
                         if (fabs(theta) > 1.0e100) t = 0.5 / theta;
                         else t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = rsqrt(t * t + 1.0);
-                        s = t * c;
+                        c_l = rsqrt(t * t + 1.0);
+                        s_l = t * c_l;
                         rotated = 1;
                     }
                 }
-                cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+                p_l = p; q_l = q;
+                cs[k] = c_l; sn[k] = s_l; pp[k] = p; qq[k] = q;       // for the column phase of the other warps
             }
-            __syncthreads();
-            // every warp owns 4 of the (at most 32) disjoint pairs; lanes run along the row / column
-            for (int kk = 0; kk < 4; kk++) {                         // rows p,q  <-  J^T A
-                const int k = (tid >> 5) * 4 + kk;
-                if (k >= h) break;
-                const double s = sn[k];
-                if (s == 0.0) continue;
-                const double c = cs[k];
-                const int p = pp[k], q = qq[k];
-                for (int j = tid & 31; j < n2; j += 32) {
+            for (int kk = 0; kk < 4; kk++) {                         // rows p,q  <-  J^T A   (own pairs)
+                const double s = __shfl_sync(0xffffffffu, s_l, kk);
+                const double c = __shfl_sync(0xffffffffu, c_l, kk);
+                const int p = __shfl_sync(0xffffffffu, p_l, kk), q = __shfl_sync(0xffffffffu, q_l, kk);
+                if (wk0 + kk >= h || s == 0.0) continue;
+                for (int j = lane; j < n2; j += 32) {
                     double ap = a[p * ELD + j], aq = a[q * ELD + j];
                     a[p * ELD + j] = c * ap - s * aq;
                     a[q * ELD + j] = s * ap + c * aq;
@@ -109,13 +111,13 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
             }
             __syncthreads();
             for (int kk = 0; kk < 4; kk++) {                         // cols p,q  <-  A J ;  V J ; pivot entries zeroed
-                const int k = (tid >> 5) * 4 + kk;
+                const int k = wk0 + kk;
                 if (k >= h) break;
                 const double s = sn[k];
                 if (s == 0.0) continue;
                 const double c = cs[k];
                 const int p = pp[k], q = qq[k];
-                for (int i = tid & 31; i < n2; i += 32) {
+                for (int i = lane; i < n2; i += 32) {
                     double ap = a[i * ELD + p], aq = a[i * ELD + q];
                     double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
                     if (i == p) nq_ = 0.0;

@@ -238,10 +238,22 @@ template <bool TA, bool TB, bool AL>
 void launch_shape(const GemmParams& p, cudaStream_t st) {
     long long tilesL = cdiv(p.M, 128) * cdiv(p.N, 128) * (long long)p.batch * p.batch2;
     if (p.lower) tilesL = tilesL / 2 + cdiv(p.M, 128);
-    if (tilesL >= 100 && p.M > 64 && p.N > 64)
+    if (tilesL >= 100 && p.M > 64 && p.N > 64) {
         launch_cfg<128, 128, 32, 3, 2, 4, TA, TB, AL>(p, st);
-    else
-        launch_cfg<64, 64, 16, 4, 2, 2, TA, TB, AL>(p, st);
+        return;
+    }
+    const long long ctasM = cdiv(p.M, 128) * cdiv(p.N, 64) * (long long)p.batch * p.batch2;
+    if (p.N <= 64 && p.M >= 512 && ctasM >= 148 && !p.lower) {
+        // tall-skinny products (block-Jacobi panel rotations, panel solves): 128 x 64 tiles, 8 warps of 32 x 32
+        launch_cfg<128, 64, 16, 3, 4, 2, TA, TB, AL>(p, st);
+        return;
+    }
+    if (p.K >= 512) {
+        // long-K small-output products (Gram matrices of the block-Jacobi panels): deeper K tiles, fewer barriers
+        launch_cfg<64, 64, 32, 3, 2, 2, TA, TB, AL>(p, st);
+        return;
+    }
+    launch_cfg<64, 64, 16, 4, 2, 2, TA, TB, AL>(p, st);
 }
 
 template <bool AL>

@@ -84,6 +84,10 @@ __global__ void k_add_diag(int m, double* A, int lda, double v) {
     int i = blockIdx.x * TB + threadIdx.x;
     if (i < m) A[(size_t)i * lda + i] += v;
 }
+__global__ void k_add_diag_vec(int m, double* A, int lda, double a, double b, const double* D) {
+    int i = blockIdx.x * TB + threadIdx.x;
+    if (i < m) A[(size_t)i * lda + i] += a * D[i] + b / D[i];
+}
 __global__ void k_set_identity(int m, double* A, int lda, double v) {
     int i = blockIdx.x * TB + threadIdx.x, j = blockIdx.y;
     if (i < m) A[(size_t)j * lda + i] = (i == j) ? v : 0.0;
@@ -333,6 +337,10 @@ void mat_transpose(cudaStream_t st, int m, double* out, int ldo, const double* i
 }
 void mat_add_diag(cudaStream_t st, int m, double* A, int lda, double v) {
     k_add_diag<<<(unsigned)cdiv(m, TB), TB, 0, st>>>(m, A, lda, v);
+    LRN_CHECK_LAUNCH();
+}
+void mat_add_diag_vec(cudaStream_t st, int m, double* A, int lda, double a, double b, const double* D) {
+    k_add_diag_vec<<<(unsigned)cdiv(m, TB), TB, 0, st>>>(m, A, lda, a, b, D);
     LRN_CHECK_LAUNCH();
 }
 void mat_set_identity(cudaStream_t st, int m, double* A, int lda, double v) {

@@ -24,6 +24,8 @@ void mat_scale_cols(cudaStream_t st, int rows, int cols, double* out, int ldo, c
 // out = in^T
 void mat_transpose(cudaStream_t st, int m, double* out, int ldo, const double* in, int ldi);
 void mat_add_diag(cudaStream_t st, int m, double* A, int lda, double v);
+// A[i,i] += a * D[i] + b / D[i]
+void mat_add_diag_vec(cudaStream_t st, int m, double* A, int lda, double a, double b, const double* D);
 void mat_set_identity(cudaStream_t st, int m, double* A, int lda, double v);
 // d[j] = sum_i A[i,j] * B[i,j]
 void mat_coldot(cudaStream_t st, int rows, int cols, const double* A, int lda, const double* B, int ldb, double* d);

@@ -242,7 +242,7 @@ void build_block(lrn_solver* h, Block& B) {
     B.normC = std::sqrt(nc);
     LRN_CUDA(cudaStreamSynchronize(h->st));
     B.hAA = HostCSC(); B.hB = HostCSC(); B.hC = HostCSC();
-    for (DMat* M : {&B.X, &B.S, &B.dX, &B.dS, &B.Xn, &B.Sn, &B.G, &B.Gi, &B.W, &B.Si, &B.Rd, &B.RNT, &B.LX, &B.LS, &B.T1, &B.T2, &B.T3})
+    for (DMat* M : {&B.X, &B.S, &B.dX, &B.dS, &B.Xn, &B.Sn, &B.G, &B.Gi, &B.W, &B.Si, &B.Rd, &B.RNT, &B.LX, &B.LS, &B.T1, &B.T2, &B.T3, &B.T4})
         M->init(m, m);
     B.ld = B.X.ld;
     B.D.alloc(m); B.DDsi.alloc(m); B.dm12.alloc(m); B.dm32.alloc(m); B.vtmp.alloc(m);
@@ -474,7 +474,7 @@ int32_t lrn_finalize(lrn_handle_t h) {
                 Block& B = h->blk[i];
                 if (B.m > 64 && B.m <= 384) {
                     h->eig_small.push_back(i);
-                    ptrs.push_back(B.T3.p()); ptrs.push_back(B.T1.p());
+                    ptrs.push_back(B.T4.p()); ptrs.push_back(B.T1.p());
                     ms.push_back(B.m); ms.push_back(B.m); lds.push_back(B.ld); lds.push_back(B.ld);
                 }
             }
@@ -580,7 +580,7 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
         Phase ph(h, LRN_T_PREPARE_W);
         cudaStream_t st = h->st;
         if (status4) *status4 = 0;
-        const double svd_tol = h->opt.svd_tol > 0 ? h->opt.svd_tol : 1e-9;
+        const double svd_tol = h->opt.svd_tol > 0 ? h->opt.svd_tol : 1e-6;
         for (auto& B : h->blk) {
             const int m = B.m, ld = B.ld;
             if (!B.chol_cached) {
@@ -813,32 +813,35 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
             // delS = Rd - mat(AA' dely)                                        (src/predictor_corrector.jl:252)
             LRN_CUDA(cudaMemcpyAsync(B.dS.p(), B.Rd.p(), B.Rd.bytes(), cudaMemcpyDeviceToDevice, st));
             sp_scatter_ATy(st, B.sp, h->dely.p, -1.0, B.dS.p(), ld);
-            // Xi = W delS W                                                    (:253)
-            gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.dS.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_nn(st, m, m, m, 1.0, B.T1.p(), ld, B.W.p(), ld, 0.0, B.T2.p(), ld);
-            if (predict) {
-                // delX = mat(-X - Xi)                                          (:255)
-                mat_sym_lincomb(st, m, B.dX.p(), ld, -1.0, B.X.p(), ld, -1.0, B.T2.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
-            } else {
-                // delX = mat(sigma mu Si - X - Xi + G RNT G')                  (:257)
-                gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.RNT.p(), ld, 0.0, B.T1.p(), ld);
-                gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.G.p(), ld, 0.0, B.T3.p(), ld);
-                mat_sym_lincomb(st, m, B.dX.p(), ld, sm, B.Si.p(), ld, -1.0, B.X.p(), ld, -1.0, B.T2.p(), ld, 1.0, B.T3.p(), ld);
-            }
-            // delXb = Gi delX Gi' ; XXX = sym(DDsi' .* delXb .* DDsi) ; eigmin  (:264,:268-272)
-            gemm_nt(st, m, m, m, 1.0, B.dX.p(), ld, B.Gi.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_nn(st, m, m, m, 1.0, B.Gi.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
-            mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
-            const bool batched = (m > 64 && m <= 384);
-            if (!batched) alpha[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
-            // delSb = G' delS G                                                (:263,:281-285)
+            // delSb = G' delS G                                                (:263)
             gemm_nn(st, m, m, m, 1.0, B.dS.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
             gemm_tn(st, m, m, m, 1.0, B.G.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
-            if (batched) {
-                mat_scaled_sym(st, m, B.T1.p(), ld, B.T2.p(), ld, B.DDsi.p);      // X part stays in T3, S part in T1
-            } else {
-                mat_scaled_sym(st, m, B.T3.p(), ld, B.T2.p(), ld, B.DDsi.p);
-                beta[i] = steplen(lambda_min(h, B.T3.p(), m, ld), tau);
+            // delX = mat(-X - W delS W)                         (predictor, :255)
+            //      = mat(sigma mu Si - X - W delS W + G RNT G') (corrector, :257)
+            // with W = G G' both congruences collapse into ONE:  delX = mat([sigma mu Si] - X + G (RNT - delSb) G')
+            if (predict) mat_lincomb(st, m, m, B.T3.p(), ld, -1.0, B.T2.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
+            else mat_lincomb(st, m, m, B.T3.p(), ld, -1.0, B.T2.p(), ld, 1.0, B.RNT.p(), ld, 0.0, nullptr, 0);
+            gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.T3.p(), ld, 0.0, B.T1.p(), ld);
+            gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.G.p(), ld, 0.0, B.T4.p(), ld);
+            if (predict)
+                mat_sym_lincomb(st, m, B.dX.p(), ld, -1.0, B.X.p(), ld, 1.0, B.T4.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
+            else
+                mat_sym_lincomb(st, m, B.dX.p(), ld, sm, B.Si.p(), ld, -1.0, B.X.p(), ld, 1.0, B.T4.p(), ld, 0.0, nullptr, 0);
+            // delXb = Gi delX Gi' (:264) in closed form (Gi X Gi' = D, Gi Si Gi' = D^-1, Gi W = G'):
+            //   delXb = (RNT - delSb) - diag(D) [+ sigma mu diag(1/D)]       -> T3
+            mat_add_diag_vec(st, m, B.T3.p(), ld, -1.0, predict ? 0.0 : sm, B.D.p);
+            if (predict) {
+                // RNT = -(Gi delX delS G + G' delS delX Gi') ./ (D_p + D_q) = -(P + P') ./ (...), P = delXb delSb   (:308-309)
+                gemm_nn(st, m, m, m, 1.0, B.T3.p(), ld, B.T2.p(), ld, 0.0, B.T1.p(), ld);
+                mat_rnt(st, m, B.RNT.p(), ld, B.T1.p(), ld, B.D.p);
+            }
+            // XXX = sym(DDsi' .* delXb .* DDsi), sym(DDsi' .* delSb .* DDsi) ; eigmin                   (:268-285)
+            mat_scaled_sym(st, m, B.T4.p(), ld, B.T3.p(), ld, B.DDsi.p);
+            mat_scaled_sym(st, m, B.T1.p(), ld, B.T2.p(), ld, B.DDsi.p);
+            const bool batched = (m > 64 && m <= 384);
+            if (!batched) {
+                alpha[i] = steplen(lambda_min(h, B.T4.p(), m, ld), tau);
+                beta[i] = steplen(lambda_min(h, B.T1.p(), m, ld), tau);
             }
         }
         if (!h->eig_small.empty()) {
@@ -873,10 +876,6 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
                 // Xn, Sn, RNT                                                   (:306-309)
                 mat_lincomb(st, m, m, B.Xn.p(), ld, 1.0, B.X.p(), ld, alpha[i], B.dX.p(), ld, 0.0, nullptr, 0);
                 mat_lincomb(st, m, m, B.Sn.p(), ld, 1.0, B.S.p(), ld, beta[i], B.dS.p(), ld, 0.0, nullptr, 0);
-                gemm_nn(st, m, m, m, 1.0, B.dX.p(), ld, B.dS.p(), ld, 0.0, B.T1.p(), ld);
-                gemm_nn(st, m, m, m, 1.0, B.Gi.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
-                gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.G.p(), ld, 0.0, B.T3.p(), ld);
-                mat_rnt(st, m, B.RNT.p(), ld, B.T3.p(), ld, B.D.p);
             }
             if (h->nlin > 0)
                 k_lp_pred_update<<<nb(h->nlin), TBK, 0, st>>>(h->nlin, *alpha_lin, *beta_lin, h->x_lin.p, h->s_lin.p, h->dx_lin.p,

@@ -26,7 +26,7 @@ struct Block {
     SparseBlock sp;
     DMat C;
     double normC = 0.0;
-    DMat X, S, dX, dS, Xn, Sn, G, Gi, W, Si, Rd, RNT, LX, LS, T1, T2, T3;
+    DMat X, S, dX, dS, Xn, Sn, G, Gi, W, Si, Rd, RNT, LX, LS, T1, T2, T3, T4;
     DevBuf<double> D, DDsi, dm12, dm32, vtmp;
     CholWork cholX, cholS;
     SvdWork svd;

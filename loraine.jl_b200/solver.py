@@ -305,13 +305,18 @@ def set_iterate(s, X, S, y, x_lin, s_lin):
     s._call("lrn_set_iterate", Xp, Sp, _dp(y), _dp(xl) if md.nlin else None, _dp(sl) if md.nlin else None)
 
 
-def get_solution(s):
+def get_solution(s, out=None):
+    """download y, X, x_lin (src/MOI_wrapper.jl:315-354 read them from the solver); `out` = (y, [X_i], x_lin) lets the caller
+    provide (e.g. pinned) Fortran-ordered destination buffers"""
     md = s.model
-    y = np.zeros(md.n)
-    X = [np.zeros((m, m), order="F") for m in md.msizes]
     PD = C.POINTER(C.c_double)
+    if out is not None:
+        y, X, xl = out
+    else:
+        y = np.zeros(md.n)
+        X = [np.zeros((m, m), order="F") for m in md.msizes]
+        xl = np.zeros(md.nlin)
     Xp = (PD * max(1, md.nlmi))(*[_dp(x) for x in X])
-    xl = np.zeros(md.nlin)
     s._call("lrn_get_solution", _dp(y), Xp, _dp(xl) if md.nlin else None)
     s.y, s.X, s.X_lin = y, X, xl
     return y, X, xl

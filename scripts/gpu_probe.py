@@ -75,7 +75,7 @@ for n in (64, 128, 256, 512, 1000, 2000, 5000, 10000):
     print("chol", n, "%.3f ms %.2f TF/s info %d" % (ms.value, tf, info.value), flush=True)
 out["cholesky"] = ch
 sv = []
-for m in (200, 801, 2000):
+for m in (200, 801, 2000, 5000):
     A = np.asfortranarray(rng.standard_normal((m, m)))
     UD, V, sg = np.asfortranarray(np.zeros((m, m))), np.asfortranarray(np.zeros((m, m))), np.zeros(m)
     sw, ms = C.c_int32(), C.c_double()

@@ -258,3 +258,75 @@ def test_cg_operator_and_preconditioner_apply(pkg):
     g._call("lrn_apply_operator", 1, dpx(x), dpx(out))
     assert relerr(out, lo.MyM(s, ha)(x)) <= 1e-6
     g.close()
+
+
+def test_regularisation_path_matches_oracle(pkg):
+    """Linearly dependent constraint matrices make H singular: the reference catches PosDefException, adds 1e-4 I until
+    `isposdef` (src/predictor_corrector.jl:59-85) and then solves with the `Cholesky` object (H^-1 H^-1 h quirk, :89-90).
+    The CUDA path must take the same branch (lrn_schur_factor > 0 -> lrn_schur_shift loop -> lrn_schur_solve(6))."""
+    from oracle import loraine_oracle as lo, sdpa_io
+    from loraine_jl_b200 import solver as S
+    n, bs, c, body = pkg.problems.large_schur(12, 20, 3)
+    body = np.array(body)
+    dup = body[body[:, 0] == 2].copy()
+    body = body[body[:, 0] != 3]
+    dup[:, 0] = 3                                   # F_3 := F_2  -> H has two identical rows/columns
+    body = np.concatenate([body, dup])
+    c = np.array(c); c[2] = c[1]
+    opts = dict(kit=0, initpoint=1, eDIMACS=1e-6, verb=0, maxit=3)
+    opt, ora = make_pair(pkg, (n, bs, c, body), opts)
+    g, s = step_both(pkg, opt, ora, 1)
+    assert s.regcount == 1 and g.regcount == 1
+    assert s.chol_is_factor_object and g.cholBBBB.is_cholesky_object
+    assert relerr(g.get_array("DELY"), s.dely) <= 1e-6
+    g.close()
+
+
+def test_non_pd_iterate_is_regularised_like_try_cholesky(pkg):
+    """src/prepare_W.jl:5-26: X not positive definite -> X += 1e-5 I until the factorisation succeeds."""
+    from loraine_jl_b200 import solver as S
+    arrays = pkg.problems.theta_torus(3, 4)
+    opt = pkg.Optimizer()
+    for k, v in dict(kit=0, initpoint=1, verb=0).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    g = opt.solver
+    S.setup_solver(g, opt.halpha)
+    S.initial_point(g)
+    m, n = g.model.msizes[0], g.model.n
+    X = np.eye(m); X[0, 0] = -2e-5                  # needs 3 shifts of 1e-5
+    S.set_iterate(g, [X], [2.0 * np.eye(m)], np.zeros(n), np.zeros(0), np.zeros(0))
+    S.find_mu(g)
+    S.prepare_W(g)
+    assert g.status == 0
+    y, Xd, _ = S.get_solution(g)
+    assert abs(Xd[0][0, 0] - (-2e-5 + 3e-5)) <= 1e-12 and abs(Xd[0][1, 1] - (1 + 3e-5)) <= 1e-12
+    W = g.get_array("W", 0)
+    assert np.all(np.isfinite(W)) and np.linalg.eigvalsh(W)[0] > 0
+    g.close()
+
+
+def test_cg_path_with_lp_block_iterations(pkg):
+    """kit = 1 with an LP block: AAAATtau is not diagonal (dense + Cholesky on the device, src/Solvers.jl:743-745,874,900).
+    Three full IP iterations (predictor + corrector PCG solves) track the oracle; in the fourth both PCGs break down
+    (exit code -13) on this instance, after which the iterates are rounding-dependent."""
+    arrays = pkg.problems.multiblock_lp(3, 12, 10, 7)
+    o = dict(kit=1, preconditioner=1, erank=1, aamat=2, initpoint=1, verb=0, eDIMACS=1e-12, tol_cg=1e-9, tol_cg_min=1e-9)
+    opt, ora = make_pair(pkg, arrays, o)     # tight CG tolerance: both sides follow the exact Newton directions
+    g, s = step_both(pkg, opt, ora, 3)
+    assert abs(g.cg_iter_tot - s.cg_iter_tot) <= max(4, 0.2 * s.cg_iter_tot)
+    assert abs(g.DIMACS_error - s.DIMACS_error) <= 1e-4 * max(1.0, s.DIMACS_error)
+    assert abs(g.primal_obj - s.primal_obj) <= 1e-4 * (1 + abs(s.primal_obj))
+    g.close()
+
+
+def test_iteration_limit_status(pkg):
+    """src/Solvers.jl:451-456: iter > maxit sets status 4 (the step still runs)."""
+    arrays = pkg.problems.theta_torus(3, 4)
+    opt = pkg.Optimizer()
+    for k, v in dict(kit=0, initpoint=1, verb=0, maxit=2).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    opt.optimize()
+    assert opt.solver.status == 4 and opt.solver.iter == 3 and opt.termination_status() == "ITERATION_LIMIT"
+    opt.solver.close()
