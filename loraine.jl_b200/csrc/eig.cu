@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
     for (int sweep = 0; sweep < P.max_sweeps; sweep++) {
         if (tid == 0) rotated = 0;
         __syncthreads();
-        for (int r = 0; r < n2 - 1; r++) {
+        const int nsteps = P.cross_only ? 32 : n2 - 1;
+        for (int r = 0; r < nsteps; r++) {
             // every warp owns 4 of the (at most 32) disjoint pairs of this step: lanes 0..3 compute the rotations of the
             // warp's own pairs (they only read rows p,q that no other warp writes in the row phase), no block barrier needed
             const int lane = tid & 31, wk0 = (tid >> 5) * 4;
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
             if (lane < 4 && wk0 + lane < h) {
                 const int k = wk0 + lane;
                 int p, q;
-                if (k == 0) { p = n2 - 1; q = r; }
+                if (P.cross_only) { p = k; q = 32 + ((k + r) & 31); }
+                else if (k == 0) { p = n2 - 1; q = r; }
                 else { p = (r + k) % (n2 - 1); q = (r - k + (n2 - 1)) % (n2 - 1); }
                 if (p > q) { int t = p; p = q; q = t; }
                 if (q < n) {
@@ -512,6 +514,7 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
             e.A = w.gram.p; e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; e.n = 64;
             e.V = w.rot.p; e.ldv = 64; e.sV = 4096; e.relative = 1; e.offmax = w.offmax.p; e.batch = pairs;
             e.max_sweeps = w.inner_sweeps;   // one cyclic sweep per visit converges in as many outer sweeps as full diagonalisation
+            e.cross_only = (nblk > 2 && r > 0) ? 1 : 0;   // pairs inside a 32-column block: once per sweep (round 0) is enough
             // note: no sorting inside the pair rotations -- with the round-robin block ordering it makes columns migrate
             // between blocks and the sweep no longer visits every column pair (observed: no convergence)
             jacobi_eig_small(e, st);
@@ -604,6 +607,7 @@ int svd_block_jacobi_batched(const double* const* A, int lda, int m, int nb, dou
             e.A = w.gram.p; e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; e.n = 64;
             e.V = w.rot.p; e.ldv = 64; e.sV = 4096; e.relative = 1; e.offmax = w.offmax.p; e.batch = np;
             e.max_sweeps = inner;
+            e.cross_only = (nblk > 2 && r > 0) ? 1 : 0;
             jacobi_eig_small(e, st);
             GemmParams u;
             u.A = cur; u.B = w.rot.p; u.C = nxt;

@@ -30,6 +30,8 @@ struct EigSmallParams {
     double* minval = nullptr;    // optional: per batch smallest eigenvalue (stride 1)
     int batch = 1;
     int max_sweeps = 40;         // cyclic sweeps over all pairs (1 = a single sweep, used inside the block-Jacobi SVD)
+    int cross_only = 0;          // n = 64 only: rotate just the 32 x 32 pairs (p < 32 <= q) in 32 steps -- the pairs inside each
+                                 // half are covered once per outer sweep by the round that runs the full schedule
 };
 void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st);
 

@@ -248,13 +248,14 @@ void build_block(lrn_solver* h, Block& B) {
     B.D.alloc(m); B.DDsi.alloc(m); B.dm12.alloc(m); B.dm32.alloc(m); B.vtmp.alloc(m);
 }
 
-// smallest eigenvalue of the symmetric m x m matrix T (device)
-double lambda_min(lrn_solver* h, const double* T, int m, int ld) {
+// smallest (and optionally largest) eigenvalue of the symmetric m x m matrix T (device)
+double lambda_min(lrn_solver* h, const double* T, int m, int ld, double* lmax = nullptr) {
     Phase ph(h, LRN_T_EIGMIN);
     double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-8;
-    LanczosResult r = lanczos_extreme(T, m, ld, 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st);
+    LanczosResult r = lanczos_extreme(T, m, ld, lmax ? 3 : 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st);
     h->stat_lanczos_iters += r.iters;
     if (!r.converged) h->stat_lanczos_fail++;
+    if (lmax) *lmax = r.lmax;
     return r.lmin;
 }
 
@@ -839,7 +840,14 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
             mat_scaled_sym(st, m, B.T4.p(), ld, B.T3.p(), ld, B.DDsi.p);
             mat_scaled_sym(st, m, B.T1.p(), ld, B.T2.p(), ld, B.DDsi.p);
             const bool batched = (m > 64 && m <= 384);
-            if (!batched) {
+            if (!batched && predict) {
+                // predictor: XXX_X = DDsi (-D - delSb) DDsi = -I - XXX_S  (diag(G'SG) = D), so eigmin(XXX_X) = -1 - eigmax(XXX_S):
+                // one Lanczos run delivers both step lengths
+                double lmax = 0.0;
+                const double lmin = lambda_min(h, B.T1.p(), m, ld, &lmax);
+                beta[i] = steplen(lmin, tau);
+                alpha[i] = steplen(-1.0 - lmax, tau);
+            } else if (!batched) {
                 alpha[i] = steplen(lambda_min(h, B.T4.p(), m, ld), tau);
                 beta[i] = steplen(lambda_min(h, B.T1.p(), m, ld), tau);
             }
