@@ -286,6 +286,7 @@ int32_t lrn_prec_prepare(lrn_handle_t h, int32_t kind) {
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(h->finalized && h->nlmi > 0, "preconditioners need at least one PSD block");
         PhaseT ph(h, LRN_T_PREC);
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         ensure_cg(h);
         int32_t rc = LRN_OK;
         if (kind == 1) rc = prec_alpha(h);
@@ -303,6 +304,7 @@ int32_t lrn_pcg(lrn_handle_t h, double tol, int64_t max_iter, int32_t kind, int6
         LRN_REQUIRE(kind == 0 || h->prec_ready == kind || (kind != 1 && (h->prec_ready == 2 || h->prec_ready == 4)),
                     "preconditioner not prepared (lrn_prec_prepare)");
         PhaseT ph(h, LRN_T_CG);
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         ensure_cg(h);
         cudaStream_t st = h->st;
         const int n = h->n_var;

@@ -614,14 +614,8 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             // G = L_X V D^{-1/2} = L_S^{-T} (U D) D^{-1/2}   (CC V = U D with CC = L_S' L_X)   (src/prepare_W.jl:60)
             mat_scale_cols(st, m, m, B.G.p(), ld, B.T2.p(), ld, B.dm12.p);
             trsm_left_lower_trans(B.LS.p(), m, ld, B.cholS, B.G.p(), ld, m, st);
-            // Gi = inv(G) = D^{-1/2} U' L_S' = (L_S (U D) D^{-3/2})'          (src/prepare_W.jl:63, closed form)
-            {
-                GemmParams p;
-                p.A = B.LS.p(); p.B = B.T2.p(); p.C = B.T1.p(); p.M = m; p.N = m; p.K = m; p.lda = ld; p.ldb = ld; p.ldc = ld;
-                p.colscale = B.dm32.p;
-                gemm(p, st);
-                mat_transpose(st, m, B.Gi.p(), ld, B.T1.p(), ld);
-            }
+            // Gi = inv(G) (src/prepare_W.jl:63) is never multiplied with anything on the device (find_step uses the closed
+            // forms of the scaled directions); it is produced on demand for the LRN_ARR_GI parity hook from U D kept in T2.
             // W = G G'                                                        (src/prepare_W.jl:64)
             gemm_nt(st, m, m, m, 1.0, B.G.p(), ld, B.G.p(), ld, 0.0, B.W.p(), ld);
             mat_symmetrize(st, m, B.W.p(), ld);
@@ -629,10 +623,10 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             mat_scale_cols(st, m, m, B.T1.p(), ld, B.G.p(), ld, B.dm12.p);
             gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.T1.p(), ld, 0.0, B.Si.p(), ld);
             mat_symmetrize(st, m, B.Si.p(), ld);
-            // DDsi = 1 ./ sqrt(diag(G' S G))                                  (src/prepare_W.jl:71-74)
-            gemm_nn(st, m, m, m, 1.0, B.S.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
-            mat_coldot(st, m, m, B.G.p(), ld, B.T1.p(), ld, B.vtmp.p);
-            vec_op(st, m, VEC_RSQRT, B.DDsi.p, B.vtmp.p, nullptr);
+            // DDsi = 1 ./ sqrt(diag(G' S G))  (src/prepare_W.jl:71-74).  With G = L_S^{-T} (U D) D^{-1/2} the p-th diagonal entry
+            // of G' S G is ||(U D)(:,p)||^2 / D_p = D_p exactly (D_p IS that column norm), so DDsi = D^{-1/2} without a GEMM.
+            LRN_CUDA(cudaMemcpyAsync(B.DDsi.p, B.dm12.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            B.ud_valid = true;        // T2 = U D and LS stay intact until the next call that uses the scratch matrices
         }
         if (h->nlin > 0) vec_op(st, h->nlin, VEC_RECIP, h->si_lin.p, h->s_lin.p, nullptr);
         return LRN_OK;
@@ -661,6 +655,7 @@ int32_t lrn_residuals(lrn_handle_t h) {
 
 int32_t lrn_schur_assemble(lrn_handle_t h) {
     return guarded(h, [&]() -> int32_t {
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
         Phase ph(h, LRN_T_ASSEMBLE);
         cudaStream_t st = h->st;
@@ -721,6 +716,7 @@ static void add_lp_rhs(lrn_solver* h, int corr, double sigmamu) {
 
 int32_t lrn_rhs_predictor(lrn_handle_t h) {
     return guarded(h, [&]() -> int32_t {
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         Phase ph(h, LRN_T_RHS);
         cudaStream_t st = h->st;
         LRN_CUDA(cudaMemcpyAsync(h->rhs.p, h->Rp.p, h->n_var * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -739,6 +735,7 @@ int32_t lrn_rhs_predictor(lrn_handle_t h) {
 
 int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
     return guarded(h, [&]() -> int32_t {
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         Phase ph(h, LRN_T_RHS);
         cudaStream_t st = h->st;
         const double sm = sigma * mu;
@@ -804,6 +801,7 @@ int32_t lrn_schur_solve(lrn_handle_t h, int32_t which) {
 int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, double tau, double* alpha, double* beta,
                       double* alpha_lin, double* beta_lin) {
     return guarded(h, [&]() -> int32_t {
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         LRN_REQUIRE((h->nlmi == 0 || (alpha && beta)) && alpha_lin && beta_lin, "null outputs");
         Phase ph(h, LRN_T_FIND_STEP);
         cudaStream_t st = h->st;
@@ -929,6 +927,7 @@ int32_t lrn_sigma_trace(lrn_handle_t h, double* tr, double* dl) {
 
 int32_t lrn_dimacs(lrn_handle_t h, double* err6, double* by_out, double* trCX_out, double* dx_out) {
     return guarded(h, [&]() -> int32_t {
+        for (auto& Bk : h->blk) Bk.ud_valid = false;
         LRN_REQUIRE(err6, "null output");
         Phase ph(h, LRN_T_DIMACS);
         cudaStream_t st = h->st;
@@ -1022,7 +1021,17 @@ int32_t lrn_get_array(lrn_handle_t h, int32_t which, int64_t iblk, double* out) 
             switch (which) {
                 case LRN_ARR_W: M = &B.W; break;
                 case LRN_ARR_G: M = &B.G; break;
-                case LRN_ARR_GI: M = &B.Gi; break;
+                case LRN_ARR_GI: {
+                    // Gi = D^{-1/2} U' L_S' = (L_S (U D) D^{-3/2})'  -- valid until the next prepare_W / find_step scratch reuse
+                    LRN_REQUIRE(B.ud_valid, "Gi is only available right after lrn_prepare_W (before any other hot-path call)");
+                    GemmParams p;
+                    p.A = B.LS.p(); p.B = B.T2.p(); p.C = B.T1.p(); p.M = B.m; p.N = B.m; p.K = B.m;
+                    p.lda = B.ld; p.ldb = B.ld; p.ldc = B.ld; p.colscale = B.dm32.p;
+                    gemm(p, st);
+                    mat_transpose(st, B.m, B.Gi.p(), B.ld, B.T1.p(), B.ld);
+                    M = &B.Gi;
+                    break;
+                }
                 case LRN_ARR_SI: M = &B.Si; break;
                 case LRN_ARR_RD: M = &B.Rd; break;
                 case LRN_ARR_DELX: M = &B.dX; break;

@@ -31,6 +31,7 @@ struct Block {
     CholWork cholX, cholS;
     SvdWork svd;
     bool chol_cached = false;
+    bool ud_valid = false;             // T2 holds U*D of the last prepare_W and LS its factor (Gi parity hook)
     // H_alpha preconditioner pieces (src/Solvers.jl:149-162 Halpha)
     DMat U, Zf, MU, ZY;                // U m x erank ; Z = chol(2 W0 + U U') lower ; work m x erank
     double tau = 0.0;
