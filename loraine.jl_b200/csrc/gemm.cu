@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     extern __shared__ __align__(16) double smem[];
 
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    if (p.lower && (m0 + BM - 1 < n0)) return;
+    if (p.lower && (p.row0 + m0 + BM - 1 < p.col0 + n0)) return;
     const int z = blockIdx.z;
     const int z1 = z / p.batch2, z2 = z - z1 * p.batch2;
     const double* __restrict__ A = p.A + (size_t)z1 * p.sA + (size_t)z2 * p.sA2;
@@ -195,6 +195,120 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed variant for the two named FP64 hot kernels (Schur SYRK with squared epilogue, Cholesky trailing update): both are
+// C (+)= f(A B^T) with MN-major operands, so one k-line of a 128-wide tile is a contiguous 1 KB segment in global memory.
+// A dedicated producer warp moves those segments with the bulk-copy engine (cp.async.bulk -> SASS UBLKCP) into the padded
+// shared-memory rows and signals mbarriers; the 8 consumer warps never touch a load instruction or a block barrier in the
+// main loop.  Full 128 x 128 tiles only (the host sends edge strips to the cp.async kernel), K % 32 == 0.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BKB = 32, STB = 3, LDT = 128 + 4;
+constexpr int BULK_STAGE_ELEMS = 2 * BKB * LDT;
+constexpr size_t BULK_SMEM = (size_t)STB * BULK_STAGE_ELEMS * sizeof(double) + 64;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "LAB_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(288) dgemm_dmma_bulk_nt_kernel(const GemmParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+    if (p.lower && (m0 + 127 < n0)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bars = sbase + (uint32_t)(STB * BULK_STAGE_ELEMS * sizeof(double));     // full[0..2], empty[0..2]
+    if (tid == 0) {
+        for (int s = 0; s < STB; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (STB + s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int KT = p.K / BKB;
+    if (warp == 8) {
+        // ---- producer warp: lane l moves k-line l of the A tile and of the B tile -----------------------------------
+        const double* Ag = p.A + m0;
+        const double* Bg = p.B + n0;
+        for (int kt = 0; kt < KT; kt++) {
+            const int s = kt % STB;
+            mbar_wait(bars + 8 * (STB + s), ((kt / STB) & 1) ^ 1);
+            if (lane == 0) mbar_expect_tx(bars + 8 * s, 2u * BKB * 128u * 8u);
+            __syncwarp();
+            const uint32_t sa = sbase + (uint32_t)((s * BULK_STAGE_ELEMS + lane * LDT) * sizeof(double));
+            const uint32_t sb = sa + (uint32_t)(BKB * LDT * sizeof(double));
+            const size_t k = (size_t)kt * BKB + lane;
+            bulk_g2s(sa, Ag + k * p.lda, 128u * 8u, bars + 8 * s);
+            bulk_g2s(sb, Bg + k * p.ldb, 128u * 8u, bars + 8 * s);
+        }
+        return;
+    }
+    // ---- consumer warps: 2 x 4 layout, warp tile 64 x 32 (identical fragment code to the cp.async kernel) -------------
+    const int wm0 = (warp / 4) * 64, wn0 = (warp % 4) * 32;
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < KT; kt++) {
+        const int s = kt % STB;
+        mbar_wait(bars + 8 * s, (kt / STB) & 1);
+        const double* sA = smem + (size_t)s * BULK_STAGE_ELEMS;
+        const double* sB = sA + BKB * LDT;
+#pragma unroll
+        for (int kk = 0; kk < BKB; kk += 4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = sA[(kk + lk) * LDT + wm0 + i * 8 + lr];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = sB[(kk + lk) * LDT + wn0 + j * 8 + lr];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (STB + s));
+    }
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int col = n0 + wn0 + j * 8 + lk * 2 + t;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = m0 + wm0 + i * 8 + lr;
+                double v = acc[i][j][t];
+                double* cp = p.C + (size_t)col * p.ldc + row;
+                if (p.mode == 1) v = v * v;
+                v *= alpha;
+                if (beta != 0.0) v += beta * (*cp);
+                *cp = v;
+            }
+        }
+    }
+}
+
 std::atomic<long long> g_launches{0};
 
 // optional per-launch profiling (bench roofline): CUDA events around every DMMA GEMM launch on its own stream
@@ -266,8 +380,59 @@ void launch_trans(const GemmParams& p, cudaStream_t st) {
 
 }  // namespace
 
+namespace {
+bool g_bulk_enabled = true;
+void launch_bulk_nt(const GemmParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(dgemm_dmma_bulk_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BULK_SMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)(p.M / 128), (unsigned)(p.N / 128));
+    const bool prof = g_prof_on && g_prof.size() < PROF_CAP;
+    ProfRec rec;
+    if (prof) {
+        LRN_CUDA(cudaEventCreate(&rec.a));
+        LRN_CUDA(cudaEventCreate(&rec.b));
+        rec.flops = 2.0 * p.M * (double)p.N * p.K * (p.lower ? 0.5 : 1.0);
+        LRN_CUDA(cudaEventRecord(rec.a, st));
+    }
+    dgemm_dmma_bulk_nt_kernel<<<grid, 288, BULK_SMEM, st>>>(p);
+    LRN_CHECK_LAUNCH();
+    if (prof) {
+        LRN_CUDA(cudaEventRecord(rec.b, st));
+        g_prof.push_back(rec);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+}  // namespace
+
+void gemm_set_bulk(bool on) { g_bulk_enabled = on; }
+
 void gemm(const GemmParams& p, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
+    // TMA (bulk copy) path: large A B^T products with 16-byte aligned MN-major operands and K % 32 == 0
+    if (g_bulk_enabled && !p.transA && p.transB && p.batch == 1 && p.batch2 == 1 && !p.colscale && !p.cblkmap && p.K >= 64 &&
+        p.K % 32 == 0 && p.M >= 1024 && p.N >= 1024 && p.row0 == 0 && p.col0 == 0 &&
+        ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && p.lda % 2 == 0 && p.ldb % 2 == 0) {
+        const int Mf = p.M / 128 * 128, Nf = p.N / 128 * 128;
+        GemmParams f = p;
+        f.M = Mf; f.N = Nf;
+        launch_bulk_nt(f, stream);
+        g_bulk_enabled = false;                  // the edge strips go through the generic path below
+        if (Mf < p.M) {                          // bottom strip: rows [Mf, M), all columns
+            GemmParams e = p;
+            e.A = p.A + Mf; e.C = p.C + Mf; e.M = p.M - Mf; e.row0 = Mf;
+            gemm(e, stream);
+        }
+        if (Nf < p.N) {                          // right strip: rows [0, Mf), columns [Nf, N)
+            GemmParams e = p;
+            e.B = p.B + Nf; e.C = p.C + (size_t)Nf * p.ldc; e.M = Mf; e.N = p.N - Nf; e.col0 = Nf;
+            gemm(e, stream);
+        }
+        g_bulk_enabled = true;
+        return;
+    }
     LRN_REQUIRE(p.A && p.B && p.C, "null operand");
     LRN_REQUIRE(p.K >= 0, "negative K");
     bool al = ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && (p.lda % 2 == 0) &&

@@ -28,6 +28,8 @@ struct GemmParams {
     // optional scatter of output columns in blocks of 32 (block-Jacobi round-robin re-arrangement):
     // dest column = cblkmap[z1*(N/32) + col/32]*32 + col%32, C batch strides ignored. N must be a multiple of 32.
     const int* cblkmap = nullptr;
+    // global offsets of the sub-problem (only used by the lower-triangle tile test when a product is split into regions)
+    int row0 = 0, col0 = 0;
 };
 
 // Enqueue on `stream`. Never synchronises.
@@ -52,6 +54,8 @@ inline void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const dou
 
 // Number of DMMA GEMM kernel launches issued so far by this process (bench `gpu_launches` bookkeeping).
 long long gemm_launch_count();
+// enable / disable the TMA (cp.async.bulk) fed kernel for large A*B^T products (default on; tests compare both paths)
+void gemm_set_bulk(bool on);
 // mode 1: start recording one CUDA-event pair per GEMM launch; mode 0: stop, synchronise and report the totals
 void gemm_profile(int mode, double* ms, double* flops, long long* launches);
 

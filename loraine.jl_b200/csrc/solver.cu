@@ -490,7 +490,7 @@ int32_t lrn_finalize(lrn_handle_t h) {
         if (h->opt.kit == 0) {
             h->H.init(n, n);
             h->L.init(n, n);
-            if (rank1) h->BG.init(n, maxm);
+            if (rank1) h->BG.init(n, round_up(maxm, 32));   // K padded to a multiple of 32 (zero columns) for the TMA-fed SYRK
         }
         LRN_CUDA(cudaStreamSynchronize(h->st));
         h->finalized = true;
@@ -581,7 +581,7 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
         Phase ph(h, LRN_T_PREPARE_W);
         cudaStream_t st = h->st;
         if (status4) *status4 = 0;
-        const double svd_tol = h->opt.svd_tol > 0 ? h->opt.svd_tol : 1e-6;
+        const double svd_tol = h->opt.svd_tol > 0 ? h->opt.svd_tol : 1e-8;
         for (auto& B : h->blk) {
             const int m = B.m, ld = B.ld;
             if (!B.chol_cached) {
@@ -668,9 +668,12 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
             if (h->opt.datarank == -1) {
                 // BBBB += ((B G)(B G)').^2                                    (src/makeBBBB.jl:7-14)
                 sp_B_times_G(st, B.sp, B.G.p(), ld, h->BG.p(), h->BG.ld);
+                const int Kp = round_up(m, 32);          // zero padding columns: K % 32 == 0 selects the TMA-fed kernel
+                if (Kp > m)
+                    LRN_CUDA(cudaMemsetAsync(h->BG.p() + (size_t)m * h->BG.ld, 0, (size_t)(Kp - m) * h->BG.ld * sizeof(double), st));
                 GemmParams p;
                 p.A = h->BG.p(); p.B = h->BG.p(); p.C = h->H.p();
-                p.M = n; p.N = n; p.K = m; p.lda = h->BG.ld; p.ldb = h->BG.ld; p.ldc = h->H.ld;
+                p.M = n; p.N = n; p.K = Kp; p.lda = h->BG.ld; p.ldb = h->BG.ld; p.ldc = h->H.ld;
                 p.transB = true; p.alpha = 1.0; p.beta = 1.0; p.mode = 1; p.lower = 1;
                 if (h->world <= 1) {
                     gemm(p, st);

@@ -56,6 +56,26 @@ def test_gemm_matches_numpy(L, M, N, K, ta, tb):
     assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want) + 1e-300
 
 
+@pytest.mark.parametrize("M,N,K,lower,mode", [(1024, 1024, 64, 0, 0), (1100, 1300, 96, 0, 0), (2000, 1030, 512, 0, 0), (1500, 1500, 256, 1, 0),
+                                              (1280, 1280, 160, 1, 1), (1300, 1300, 32 * 7, 1, 1)])
+def test_gemm_tma_bulk_path(L, M, N, K, lower, mode):
+    """A B^T products with K % 32 == 0 and M, N >= 1024 run on the TMA-fed kernel (cp.async.bulk + mbarrier producer warp) for
+    the full 128 x 128 tiles and on the cp.async kernel for the edge strips; both regions are checked against NumPy."""
+    rng = np.random.default_rng(M + N + K)
+    A, B = rng.standard_normal((M, K)), rng.standard_normal((N, K))
+    if lower:
+        B = A[:N]
+    C0 = rng.standard_normal((M, N))
+    P = A @ B.T
+    want = C0 + (P ** 2 if mode else -0.75 * P)
+    got = run_gemm(L, A, B, C0, 0, 1, 1.0 if mode else -0.75, 1.0, mode=mode, lower=lower)
+    if lower:
+        il = np.tril_indices(min(M, N))
+        assert np.linalg.norm(got[il] - want[il]) <= 1e-13 * np.linalg.norm(want[il])
+    else:
+        assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want)
+
+
 def test_gemm_unaligned_colscale_beta0_nan_safe(L):
     rng = np.random.default_rng(5)
     A, B = rng.standard_normal((123, 77)), rng.standard_normal((77, 95))

@@ -330,3 +330,68 @@ def test_iteration_limit_status(pkg):
     opt.optimize()
     assert opt.solver.status == 4 and opt.solver.iter == 3 and opt.termination_status() == "ITERATION_LIMIT"
     opt.solver.close()
+
+
+def test_maxG11_rank_one_end_to_end(pkg, golden_dir):
+    """SDPLIB maxG11 (m = n_var = 800) through the rank-one Schur path (datarank = -1): SDPLIB optimum 629.1648, oracle
+    iteration count +-1 (examples/solve_sdpa.jl:30 suggests exactly this instance for datarank = -1)."""
+    z, arrays = golden(golden_dir, "maxG11")
+    opt = pkg.Optimizer()
+    for k, v in dict(OPTS_SDPA, datarank=-1).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    opt.optimize()
+    s = opt.solver
+    assert s.status == 1
+    assert abs(s.iter - int(z["oracle_iters"])) <= 1
+    assert abs(s.primal_obj - 629.1648) <= 1e-6 * 629.1648 * 10
+    assert abs(s.primal_obj - float(z["oracle_obj"])) <= 1e-6 * (1 + abs(float(z["oracle_obj"])))
+    s.close()
+
+
+def test_theta_torus_full_size_known_optimum(pkg):
+    """configs[2] at full size (m = 801, n_var = 2401, kit = 1, H_alpha): the Lovasz theta number of an even x even torus
+    (bipartite, vertex transitive) is N/2 = 400 -- a size-independent known answer (SDPLIB thetaG11 = 400.00)."""
+    c = pkg.problems.CONFIGS["C3"]
+    opt = pkg.Optimizer()
+    for k, v in dict(c["options"], verb=0).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*c["gen"]()))
+    opt.optimize()
+    s = opt.solver
+    assert s.status == 1
+    assert abs(s.primal_obj - 400.0) <= 400.0 * 2e-5            # eDIMACS = 1e-5
+    assert abs(s.dual_obj - 400.0) <= 400.0 * 1e-4
+    assert s.iter <= 40 and s.cg_iter_tot > 0
+    s.close()
+
+
+def test_large_blocks_properties_C2_quarter(pkg):
+    """size-independent properties on a 25 x 50 max-cut instance (m = 1250, multi-pair block-Jacobi + Lanczos paths):
+    W S W = X, G' S G = D, G Gi = I, H symmetric positive definite with H = W.^2 for F_k = e_k e_k'."""
+    from loraine_jl_b200 import solver as S
+    arrays = pkg.problems.maxcut_torus(25, 50, 5000)
+    opt = pkg.Optimizer()
+    for k, v in dict(kit=0, datarank=-1, initpoint=1, verb=0).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    g = opt.solver
+    S.setup_solver(g, opt.halpha); S.initial_point(g)
+    for _ in range(2):
+        S.myIPstep(g, opt.halpha); g.itertime = 0.0; S.check_convergence(g)
+    S.find_mu(g); S.prepare_W(g)
+    W, G, Gi, D = g.get_array("W", 0), g.get_array("G", 0), g.get_array("GI", 0), g.get_array("D", 0)
+    y, X, _ = S.get_solution(g)
+    import ctypes as C
+    m = g.model.msizes[0]
+    Sm = [np.zeros((m, m), order="F")]
+    Sp = (C.POINTER(C.c_double) * 1)(Sm[0].ctypes.data_as(C.POINTER(C.c_double)))
+    g._call("lrn_get_slack", Sp, None)
+    assert relerr(W @ Sm[0] @ W, X[0]) <= 1e-10
+    assert relerr(G.T @ Sm[0] @ G, np.diag(D)) <= 1e-10
+    assert np.linalg.norm(G @ Gi - np.eye(m)) <= 1e-9 * m
+    g._call("lrn_residuals"); g._call("lrn_schur_assemble")
+    H = g.get_array("H")
+    assert relerr(H, W ** 2) <= 1e-11                          # b_k = e_k  =>  H = (W).^2
+    assert g._call("lrn_schur_factor") == 0
+    g.close()
