@@ -18,7 +18,7 @@ int32_t lrn_dbg_gemm(int32_t M, int32_t N, int32_t K, int32_t transA, int32_t tr
 int32_t lrn_dbg_cholesky(int32_t n, double* A, double* x, int32_t which, int32_t* info, int32_t reps, double* ms_factor);
 /* symmetric n <= 64: eigenvalues (descending) and eigenvectors */
 int32_t lrn_dbg_eig_small(int32_t n, const double* A, double* evals, double* V, int32_t relative);
-/* one-sided block Jacobi SVD of the m x m matrix A: UD = U*diag(sigma), V, sigma (descending) */
+/* one-sided block Jacobi SVD of the m x m matrix A: UD = U*diag(sigma), V (NULL: not accumulated), sigma (descending) */
 int32_t lrn_dbg_svd(int32_t m, const double* A, double* UD, double* V, double* sigma, double tol, int32_t* sweeps, double* ms);
 /* Lanczos extreme eigenpairs of the symmetric m x m matrix T */
 int32_t lrn_dbg_lanczos(int32_t m, const double* T, int32_t nev_top, double tol, double* lmin, double* lmax,

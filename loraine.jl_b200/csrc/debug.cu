@@ -168,22 +168,23 @@ int32_t lrn_dbg_eig_small(int32_t n, const double* A, double* evals, double* V, 
 
 int32_t lrn_dbg_svd(int32_t m, const double* A, double* UD, double* V, double* sigma, double tol, int32_t* sweeps, double* ms) {
     return guard([&]() -> int32_t {
-        HostMat dA(A, m, m), dU(nullptr, m, m), dV(nullptr, m, m);
+        HostMat dA(A, m, m), dU(nullptr, m, m), dV(nullptr, V ? m : 1, V ? m : 1);
         DevBuf<double> sg(m);
         SvdWork w;
         cudaStream_t st = 0;
         cudaEvent_t e0, e1;
         LRN_CUDA(cudaEventCreate(&e0)); LRN_CUDA(cudaEventCreate(&e1));
-        w.ensure(m);
+        w.ensure(m, V != nullptr);
         LRN_CUDA(cudaEventRecord(e0, st));
-        int sw = svd_block_jacobi(dA.p, dA.ld, m, dU.p, dU.ld, dV.p, dV.ld, sg.p, w, tol > 0 ? tol : 1e-9, 30, st);
+        int sw = svd_block_jacobi(dA.p, dA.ld, m, dU.p, dU.ld, V ? dV.p : nullptr, dV.ld, sg.p, w, tol > 0 ? tol : 1e-9, 30, st);
         LRN_CUDA(cudaEventRecord(e1, st));
         LRN_CUDA(cudaDeviceSynchronize());
         float t = 0;
         LRN_CUDA(cudaEventElapsedTime(&t, e0, e1));
         if (ms) *ms = t;
         if (sweeps) *sweeps = sw;
-        dU.download(UD); dV.download(V);
+        dU.download(UD);
+        if (V) dV.download(V);
         LRN_CUDA(cudaMemcpy(sigma, sg.p, m * sizeof(double), cudaMemcpyDeviceToHost));
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return LRN_OK;

@@ -30,13 +30,32 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
     const int n = P.n, n2 = (n + 1) & ~1, h = n2 >> 1;
     const double* Az = P.A + (size_t)z * P.sA;
 
-    for (int idx = tid; idx < EN * EN; idx += 256) {
-        int i = idx % EN, j = idx / EN;
-        double val = 0.0;
-        if (i < n && j < n)
+    if (P.dg_in) {
+        // diagonal blocks from the previous round's rotated Gram matrices, cross block from the split-K partial products
+        const double* d0 = P.dg_in + (size_t)(2 * z) * 1024;
+        const double* d1 = d0 + 1024;
+        for (int idx = tid; idx < 1024; idx += 256) {
+            int i = idx & 31, j = idx >> 5;
+            a[i * ELD + j] = d0[idx];
+            a[(32 + i) * ELD + 32 + j] = d1[idx];
+            double val = 0.0;
             for (int t = 0; t < P.nparts; t++) val += Az[(size_t)t * P.sPart + (size_t)j * P.lda + i];
-        a[i * ELD + j] = val;
-        v[i * ELD + j] = (i == j) ? 1.0 : 0.0;
+            a[(32 + i) * ELD + j] = val;
+            a[j * ELD + 32 + i] = val;
+        }
+        for (int idx = tid; idx < EN * EN; idx += 256) {
+            int i = idx % EN, j = idx / EN;
+            v[i * ELD + j] = (i == j) ? 1.0 : 0.0;
+        }
+    } else {
+        for (int idx = tid; idx < EN * EN; idx += 256) {
+            int i = idx % EN, j = idx / EN;
+            double val = 0.0;
+            if (i < n && j < n)
+                for (int t = 0; t < P.nparts; t++) val += Az[(size_t)t * P.sPart + (size_t)j * P.lda + i];
+            a[i * ELD + j] = val;
+            v[i * ELD + j] = (i == j) ? 1.0 : 0.0;
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < EN * EN; idx += 256) {
@@ -165,11 +184,127 @@ __global__ void __launch_bounds__(256) jacobi_eig64_kernel(const EigSmallParams 
         }
     }
     __syncthreads();
+    if (P.dg_out) {
+        double* o0 = P.dg_out + (size_t)P.slotmap[2 * z] * 1024;
+        double* o1 = P.dg_out + (size_t)P.slotmap[2 * z + 1] * 1024;
+        for (int idx = tid; idx < 1024; idx += 256) {
+            int i = idx & 31, j = idx >> 5;
+            o0[idx] = 0.5 * (a[i * ELD + j] + a[j * ELD + i]);
+            o1[idx] = 0.5 * (a[(32 + i) * ELD + 32 + j] + a[(32 + j) * ELD + 32 + i]);
+        }
+    }
     if (P.V) {
         double* Vz = P.V + (size_t)z * P.sV;
         for (int idx = tid; idx < n * n; idx += 256) {
             int i = idx % n, j = idx / n;
             Vz[(size_t)pp[j] * P.ldv + i] = v[i * ELD + j];
+        }
+    }
+}
+
+
+// Cross-pair sweep of a 64 x 64 pair matrix (block-Jacobi rounds > 0): 32 steps, step r rotates the 32 disjoint index
+// pairs (k, 32 + (k + r) mod 32).  1024 threads: thread (ki, kj) owns the 2 x 2 block {p_i, q_i} x {p_j, q_j}, which the
+// two-sided update J' A J maps onto itself, so a step needs no intermediate barrier between the row and the column
+// rotation: warp 0 computes the 32 rotations, one barrier, every thread rotates its blocks of A and V, one barrier.
+__global__ void __launch_bounds__(1024) jacobi_cross64_kernel(const EigSmallParams P) {
+    extern __shared__ double sm[];
+    double* a = sm;
+    double* v = sm + EN * ELD;
+    double* cs = v + EN * ELD;      // 32
+    double* sn = cs + 32;           // 32
+    const int tid = threadIdx.x, z = blockIdx.x, lane = tid & 31;
+    const double* Az = P.A + (size_t)z * P.sA;
+
+    if (P.dg_in) {
+        const double* d0 = P.dg_in + (size_t)(2 * z) * 1024;
+        const double* d1 = d0 + 1024;
+        const int i = tid & 31, j = tid >> 5;
+        a[i * ELD + j] = d0[tid];
+        a[(32 + i) * ELD + 32 + j] = d1[tid];
+        double val = 0.0;
+        for (int t = 0; t < P.nparts; t++) val += Az[(size_t)t * P.sPart + (size_t)j * P.lda + i];
+        a[(32 + i) * ELD + j] = val;
+        a[j * ELD + 32 + i] = val;
+    } else {
+        for (int idx = tid; idx < EN * EN; idx += 1024) {
+            const int i = idx & 63, j = idx >> 6;
+            if (i >= j) {
+                double lo = 0.0, up = 0.0;
+                for (int t = 0; t < P.nparts; t++) {
+                    lo += Az[(size_t)t * P.sPart + (size_t)j * P.lda + i];
+                    up += Az[(size_t)t * P.sPart + (size_t)i * P.lda + j];
+                }
+                const double val = 0.5 * (lo + up);
+                a[i * ELD + j] = val;
+                a[j * ELD + i] = val;
+            }
+        }
+    }
+    for (int idx = tid; idx < EN * EN; idx += 1024) {
+        const int i = idx & 63, j = idx >> 6;
+        v[i * ELD + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (P.offmax) {
+        double lmax = 0.0;
+        for (int idx = tid; idx < EN * EN; idx += 1024) {
+            const int i = idx & 63, j = idx >> 6;
+            const double x = a[i * ELD + j];
+            if (i < j && x != 0.0) {
+                const double den = sqrt(fabs(a[i * ELD + i] * a[j * ELD + j]));
+                lmax = fmax(lmax, (den > 0.0) ? fabs(x) / den : 1.0e300);
+            }
+        }
+        lmax = warp_max(lmax);
+        if (lane == 0 && lmax > 0.0) atomic_max_nonneg(P.offmax, fmin(lmax, 1.0e300));
+    }
+    const int ki = tid >> 5, kj = lane;
+    for (int r = 0; r < 32; r++) {
+        if (tid < 32) {
+            const int p = tid, q = 32 + ((tid + r) & 31);
+            const double apq = a[p * ELD + q], app = a[p * ELD + p], aqq = a[q * ELD + q];
+            double c = 1.0, s = 0.0;
+            if (fabs(apq) > 1.0e-15 * sqrt(fabs(app * aqq))) {
+                // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq), without forming theta
+                const double d = aqq - app, x = 2.0 * apq;
+                const double h = sqrt(d * d + x * x);
+                const double t = x / (d + copysign(h, d));
+                c = rsqrt(t * t + 1.0);
+                s = t * c;
+            }
+            cs[tid] = c;
+            sn[tid] = s;
+        }
+        __syncthreads();
+        {
+            const int pi = ki, qi = 32 + ((ki + r) & 31), pj = kj, qj = 32 + ((kj + r) & 31);
+            const double ci = cs[ki], si = sn[ki], cj = cs[kj], sj = sn[kj];
+            const double x11 = a[pi * ELD + pj], x12 = a[pi * ELD + qj], x21 = a[qi * ELD + pj], x22 = a[qi * ELD + qj];
+            const double y11 = ci * x11 - si * x21, y12 = ci * x12 - si * x22;
+            const double y21 = si * x11 + ci * x21, y22 = si * x12 + ci * x22;
+            double z11 = cj * y11 - sj * y12, z12 = sj * y11 + cj * y12;
+            double z21 = cj * y21 - sj * y22, z22 = sj * y21 + cj * y22;
+            if (ki == kj && si != 0.0) { z12 = 0.0; z21 = 0.0; }
+            a[pi * ELD + pj] = z11; a[pi * ELD + qj] = z12; a[qi * ELD + pj] = z21; a[qi * ELD + qj] = z22;
+            const double v11 = v[pi * ELD + pj], v12 = v[pi * ELD + qj], v21 = v[qi * ELD + pj], v22 = v[qi * ELD + qj];
+            v[pi * ELD + pj] = cj * v11 - sj * v12; v[pi * ELD + qj] = sj * v11 + cj * v12;
+            v[qi * ELD + pj] = cj * v21 - sj * v22; v[qi * ELD + qj] = sj * v21 + cj * v22;
+        }
+        __syncthreads();
+    }
+    if (P.dg_out) {
+        double* o0 = P.dg_out + (size_t)P.slotmap[2 * z] * 1024;
+        double* o1 = P.dg_out + (size_t)P.slotmap[2 * z + 1] * 1024;
+        const int i = tid & 31, j = tid >> 5;
+        o0[tid] = 0.5 * (a[i * ELD + j] + a[j * ELD + i]);
+        o1[tid] = 0.5 * (a[(32 + i) * ELD + 32 + j] + a[(32 + j) * ELD + 32 + i]);
+    }
+    if (P.V) {
+        double* Vz = P.V + (size_t)z * P.sV;
+        for (int idx = tid; idx < EN * EN; idx += 1024) {
+            const int i = idx & 63, j = idx >> 6;
+            Vz[(size_t)j * P.ldv + i] = v[i * ELD + j];
         }
     }
 }
@@ -442,6 +577,16 @@ void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st) {
         LRN_CUDA(cudaFuncSetAttribute(jacobi_eig64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
         configured = true;
     }
+    if (p.cross_only && p.n == EN && p.relative && p.max_sweeps == 1 && !p.evals && !p.minval && !p.sort_desc) {
+        static bool configured_x = false;
+        if (!configured_x) {
+            LRN_CUDA(cudaFuncSetAttribute(jacobi_cross64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
+            configured_x = true;
+        }
+        jacobi_cross64_kernel<<<p.batch, 1024, EIG_SMEM, st>>>(p);
+        LRN_CHECK_LAUNCH();
+        return;
+    }
     jacobi_eig64_kernel<<<p.batch, 256, EIG_SMEM, st>>>(p);
     LRN_CHECK_LAUNCH();
 }
@@ -451,7 +596,9 @@ void SvdWork::ensure(int m_, bool want_V_) {
     m = m_;
     want_V = want_V_;
     mp = round_up(m, 64);
-    ldw = pad_ld(want_V ? m + mp : m);
+    const int rows_ = want_V ? m + mp : m;
+    panel = rows_ >= 1024;                         // persistent TMA panel-rotation kernel: rows padded to whole 128-row tiles
+    ldw = panel ? round_up(rows_, 128) + 8 : pad_ld(rows_);
     size_t elems = (size_t)ldw * mp;
     buf0.alloc(elems);
     buf1.alloc(elems);
@@ -461,8 +608,14 @@ void SvdWork::ensure(int m_, bool want_V_) {
     if (Kc < 64) Kc = 64;
     splits = (int)cdiv(m, Kc);
     if (splits == 1) Kc = m;
-    gram.alloc((size_t)pairs * splits * 64 * 64);
+    xsplits = (int)std::min<long long>(16, std::max<long long>(1, cdiv(444, pairs)));  // 3 CTAs per SM in the cross Gram GEMM
+    xKc = round_up((int)cdiv(m, xsplits), 32);
+    if (xKc < 256) xKc = 256;
+    xsplits = (int)cdiv(m, xKc);
+    gram.alloc((size_t)pairs * std::max(splits * 4096, xsplits * 1024));
     rot.alloc((size_t)pairs * 64 * 64);
+    dg0.alloc((size_t)nblk * 1024);
+    dg1.alloc((size_t)nblk * 1024);
     offmax.alloc(1);
     sv.alloc(mp);
     perm.alloc(mp);
@@ -497,33 +650,57 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
         svd_init_kernel<<<grid, 256, 0, st>>>(A, lda, m, mp, rows, cur, ldw);
         LRN_CHECK_LAUNCH();
     }
-    const int splits = w.splits, Kc = w.Kc;
+    const int splits = w.splits, Kc = w.Kc, xsplits = w.xsplits, xKc = w.xKc;
+    const bool recycle = nblk > 2 && m >= 256;   // hand the diagonal Gram blocks from round to round (see EigSmallParams)
+    double* dgc = w.dg0.p;
+    double* dgn = w.dg1.p;
     int sweeps = 0;
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         LRN_CUDA(cudaMemsetAsync(w.offmax.p, 0, sizeof(double), st));
         for (int r = 0; r < rounds; r++) {
-            GemmParams g;                       // Gram matrices of all column-block pairs (split-K partials)
-            g.A = cur; g.B = cur; g.C = w.gram.p;
+            // Gram matrices of all column-block pairs (split-K partials).  The first round of a sweep forms the full 64 x 64
+            // products from the columns (this also bounds the drift of the recycled diagonal blocks to one sweep); the other
+            // rounds only need the 32 x 32 cross block B_{2z+1}' B_{2z}
+            const bool cross = recycle && r > 0;
+            GemmParams g;
+            g.A = cross ? cur + (size_t)32 * ldw : cur; g.B = cur; g.C = w.gram.p;
             g.transA = true; g.transB = false;
-            g.M = 64; g.N = 64; g.K = Kc; g.lda = ldw; g.ldb = ldw; g.ldc = 64;
-            g.batch = pairs; g.sA = (long long)64 * ldw; g.sB = (long long)64 * ldw; g.sC = (long long)splits * 4096;
-            g.batch2 = splits; g.sA2 = Kc; g.sB2 = Kc; g.sC2 = 4096;
-            g.K_last = m - (splits - 1) * Kc;
+            g.lda = ldw; g.ldb = ldw;
+            g.batch = pairs; g.sA = (long long)64 * ldw; g.sB = (long long)64 * ldw;
+            if (cross) {
+                g.M = 32; g.N = 32; g.K = xKc; g.ldc = 32; g.sC = (long long)xsplits * 1024;
+                g.batch2 = xsplits; g.sA2 = xKc; g.sB2 = xKc; g.sC2 = 1024;
+                g.K_last = m - (xsplits - 1) * xKc;
+            } else {
+                g.M = 64; g.N = 64; g.K = Kc; g.ldc = 64; g.sC = (long long)splits * 4096;
+                g.batch2 = splits; g.sA2 = Kc; g.sB2 = Kc; g.sC2 = 4096;
+                g.K_last = m - (splits - 1) * Kc;
+            }
             gemm(g, st);
             EigSmallParams e;
-            e.A = w.gram.p; e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; e.n = 64;
+            e.A = w.gram.p; e.n = 64;
+            if (cross) { e.lda = 32; e.sA = (long long)xsplits * 1024; e.nparts = xsplits; e.sPart = 1024; e.dg_in = dgc; }
+            else { e.lda = 64; e.sA = (long long)splits * 4096; e.nparts = splits; e.sPart = 4096; }
+            if (recycle) { e.dg_out = dgn; e.slotmap = w.slotmap.p; std::swap(dgc, dgn); }
             e.V = w.rot.p; e.ldv = 64; e.sV = 4096; e.relative = 1; e.offmax = w.offmax.p; e.batch = pairs;
             e.max_sweeps = w.inner_sweeps;   // one cyclic sweep per visit converges in as many outer sweeps as full diagonalisation
             e.cross_only = (nblk > 2 && r > 0) ? 1 : 0;   // pairs inside a 32-column block: once per sweep (round 0) is enough
             // note: no sorting inside the pair rotations -- with the round-robin block ordering it makes columns migrate
             // between blocks and the sweep no longer visits every column pair (observed: no convergence)
             jacobi_eig_small(e, st);
-            GemmParams u;                       // rotate [A;V] panels and scatter them to next round's arrangement
-            u.A = cur; u.B = w.rot.p; u.C = nxt;
-            u.M = rows; u.N = 64; u.K = 64; u.lda = ldw; u.ldb = 64; u.ldc = ldw;
-            u.batch = pairs; u.sA = (long long)64 * ldw; u.sB = 4096;
-            u.cblkmap = w.slotmap.p;
-            gemm(u, st);
+            if (w.panel) {                      // rotate [A;V] panels and scatter them to next round's arrangement
+                PanelRotateParams u;
+                u.cur = cur; u.nxt = nxt; u.rot = w.rot.p; u.slotmap = w.slotmap.p; u.ldw = ldw;
+                u.tiles = (int)cdiv(rows, 128); u.total = (long long)u.tiles * pairs;
+                panel_rotate(u, st);
+            } else {
+                GemmParams u;
+                u.A = cur; u.B = w.rot.p; u.C = nxt;
+                u.M = rows; u.N = 64; u.K = 64; u.lda = ldw; u.ldb = 64; u.ldc = ldw;
+                u.batch = pairs; u.sA = (long long)64 * ldw; u.sB = 4096;
+                u.cblkmap = w.slotmap.p;
+                gemm(u, st);
+            }
             std::swap(cur, nxt);
         }
         sweeps++;

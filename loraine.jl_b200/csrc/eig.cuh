@@ -32,6 +32,13 @@ struct EigSmallParams {
     int max_sweeps = 40;         // cyclic sweeps over all pairs (1 = a single sweep, used inside the block-Jacobi SVD)
     int cross_only = 0;          // n = 64 only: rotate just the 32 x 32 pairs (p < 32 <= q) in 32 steps -- the pairs inside each
                                  // half are covered once per outer sweep by the round that runs the full schedule
+    // block-Jacobi SVD bookkeeping (n = 64): the two diagonal 32 x 32 blocks of the rotated matrix J'AJ are the Gram
+    // matrices of the two rotated column blocks; they are handed to the pairs of the next round through a per-slot store
+    // so that only the 32 x 32 cross block has to be recomputed from the columns.
+    double* dg_out = nullptr;        // nslots * 1024 (slot = slotmap[2z], slotmap[2z+1])
+    const int* slotmap = nullptr;
+    const double* dg_in = nullptr;   // non-null: A holds only the cross block B_{2z+1}' B_{2z} (32 x 32, lda, partials);
+                                     // the diagonal blocks come from dg_in[2z], dg_in[2z+1]
 };
 void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st);
 
@@ -45,9 +52,12 @@ struct SvdWork {
     DevBuf<int> slotmap;         // mp/32 : round-robin slot permutation
     DevBuf<double> sv;           // mp singular values (unsorted)
     DevBuf<int> perm;            // mp
-    int splits = 1, Kc = 0;
+    DevBuf<double> dg0, dg1;     // per-slot 32 x 32 Gram blocks handed from round to round (ping-pong)
+    int splits = 1, Kc = 0;      // split-K of the full 64 x 64 Gram products (first round of a sweep)
+    int xsplits = 1, xKc = 0;    // split-K of the 32 x 32 cross products (all other rounds)
     int inner_sweeps = 1;
     bool want_V = true;
+    bool panel = false;          // rows padded to 128-row tiles, panel_rotate kernel for the updates
     void ensure(int m_, bool want_V_ = true);
 };
 

@@ -309,6 +309,108 @@ __global__ void __launch_bounds__(288) dgemm_dmma_bulk_nt_kernel(const GemmParam
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Panel rotation of the block-Jacobi SVD:  nxt[:, slot(2z), slot(2z+1)] = cur[:, 64z .. 64z+63] * J_z  for every pair z.
+// Persistent CTAs walk a flattened (pair, 128-row tile) list.  The 64 x 64 rotation J_z stays resident in shared memory
+// while the producer warp streams the 128 x 64 panel tiles through a two-stage bulk-copy (TMA) ring; the eight consumer
+// warps (4 x 2, warp tile 32 x 32) run 256 DMMAs per tile and scatter the rotated columns straight from registers to the
+// slots the round-robin ordering assigns them in the next round.  Rows are padded to whole tiles (zero rows stay zero).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PR_LDA = 128 + 4, PR_LDJ = 64 + 4, PR_ST = 2;
+constexpr int PR_A_ELEMS = 64 * PR_LDA, PR_J_ELEMS = 64 * PR_LDJ;
+constexpr size_t PR_SMEM = (size_t)(PR_ST * PR_A_ELEMS + PR_J_ELEMS) * sizeof(double) + 64;
+
+__global__ void __launch_bounds__(288) panel_rotate_kernel(const PanelRotateParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t sJ_addr = sbase + (uint32_t)(PR_ST * PR_A_ELEMS * sizeof(double));
+    const uint32_t bars = sJ_addr + (uint32_t)(PR_J_ELEMS * sizeof(double));
+    const uint32_t jfull = bars + 8 * (2 * PR_ST), jempty = jfull + 8;     // full[s] = bars + 8 s, empty[s] = bars + 8 (ST + s)
+    if (tid == 0) {
+        for (int s = 0; s < PR_ST; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (PR_ST + s), 8); }
+        mbar_init(jfull, 1);
+        mbar_init(jempty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long t0 = (long long)blockIdx.x * p.total / gridDim.x, t1 = (long long)(blockIdx.x + 1) * p.total / gridDim.x;
+    if (warp == 8) {
+        int prevz = -1, jl = 0, i = 0;
+        for (long long t = t0; t < t1; t++, i++) {
+            const int z = (int)(t / p.tiles), tile = (int)(t - (long long)z * p.tiles);
+            if (z != prevz) {
+                mbar_wait(jempty, (jl & 1) ^ 1);
+                if (lane == 0) mbar_expect_tx(jfull, 64u * 64u * 8u);
+                __syncwarp();
+                const double* Jg = p.rot + (size_t)z * 4096;
+                for (int l = lane; l < 64; l += 32)
+                    bulk_g2s(sJ_addr + (uint32_t)(l * PR_LDJ * sizeof(double)), Jg + l * 64, 64u * 8u, jfull);
+                jl++;
+                prevz = z;
+            }
+            const int s = i % PR_ST;
+            mbar_wait(bars + 8 * (PR_ST + s), ((i / PR_ST) & 1) ^ 1);
+            if (lane == 0) mbar_expect_tx(bars + 8 * s, 64u * 128u * 8u);
+            __syncwarp();
+            const double* Ag = p.cur + (size_t)z * 64 * p.ldw + (size_t)tile * 128;
+            const uint32_t sa = sbase + (uint32_t)(s * PR_A_ELEMS * sizeof(double));
+            for (int l = lane; l < 64; l += 32)
+                bulk_g2s(sa + (uint32_t)(l * PR_LDA * sizeof(double)), Ag + (size_t)l * p.ldw, 128u * 8u, bars + 8 * s);
+        }
+        return;
+    }
+    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;
+    const int lr = lane >> 2, lk = lane & 3;
+    const double* sJ = smem + PR_ST * PR_A_ELEMS;
+    int prevz = -1, jl = 0, i = 0;
+    for (long long t = t0; t < t1; t++, i++) {
+        const int z = (int)(t / p.tiles), tile = (int)(t - (long long)z * p.tiles);
+        if (z != prevz) {
+            mbar_wait(jfull, jl & 1);
+            jl++;
+            prevz = z;
+        }
+        const int s = i % PR_ST;
+        mbar_wait(bars + 8 * s, (i / PR_ST) & 1);
+        const double* sA = smem + (size_t)s * PR_A_ELEMS;
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 4
+        for (int kk = 0; kk < 64; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) a[q] = sA[(kk + lk) * PR_LDA + wm0 + q * 8 + lr];
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[q] = sJ[(wn0 + q * 8 + lr) * PR_LDJ + kk + lk];
+#pragma unroll
+            for (int a_ = 0; a_ < 4; a_++)
+#pragma unroll
+                for (int b_ = 0; b_ < 4; b_++) dmma884(acc[a_][b_][0], acc[a_][b_][1], a[a_], b[b_]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bars + 8 * (PR_ST + s));
+            if (t + 1 == t1 || (int)((t + 1) / p.tiles) != z) mbar_arrive(jempty);
+        }
+        // both 32-column halves of the pair go to their own slot of the next arrangement
+        const int slot = p.slotmap[2 * z + (warp & 1)];
+        double* Cz = p.nxt + (size_t)slot * 32 * p.ldw + (size_t)tile * 128 + wm0 + lr;
+#pragma unroll
+        for (int b_ = 0; b_ < 4; b_++)
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                double* cc = Cz + (size_t)(b_ * 8 + lk * 2 + u) * p.ldw;
+#pragma unroll
+                for (int a_ = 0; a_ < 4; a_++) cc[a_ * 8] = acc[a_][b_][u];
+            }
+    }
+}
+
 std::atomic<long long> g_launches{0};
 
 // optional per-launch profiling (bench roofline): CUDA events around every DMMA GEMM launch on its own stream
@@ -362,6 +464,11 @@ void launch_shape(const GemmParams& p, cudaStream_t st) {
         launch_cfg<128, 64, 16, 3, 4, 2, TA, TB, AL>(p, st);
         return;
     }
+    if (p.M <= 32 && p.N <= 32 && p.K >= 256) {
+        // 32 x 32 cross Gram blocks of the block-Jacobi SVD (split-K batches): the product streams its operands once
+        launch_cfg<32, 32, 32, 4, 2, 2, TA, TB, AL>(p, st);
+        return;
+    }
     if (p.K >= 512) {
         // long-K small-output products (Gram matrices of the block-Jacobi panels): deeper K tiles, fewer barriers
         launch_cfg<64, 64, 32, 3, 2, 2, TA, TB, AL>(p, st);
@@ -406,6 +513,36 @@ void launch_bulk_nt(const GemmParams& p, cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 }  // namespace
+
+void panel_rotate(const PanelRotateParams& p, cudaStream_t st) {
+    static bool configured = false;
+    static int sms = 148;
+    if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(panel_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_SMEM));
+        int dev = 0;
+        LRN_CUDA(cudaGetDevice(&dev));
+        LRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    LRN_REQUIRE(p.ldw % 2 == 0 && p.tiles * 128 <= p.ldw, "panel_rotate: rows must be padded to whole 128-row tiles");
+    if (p.total <= 0) return;
+    const bool prof = g_prof_on && g_prof.size() < PROF_CAP;
+    ProfRec rec;
+    if (prof) {
+        LRN_CUDA(cudaEventCreate(&rec.a));
+        LRN_CUDA(cudaEventCreate(&rec.b));
+        rec.flops = 2.0 * 128.0 * 64.0 * 64.0 * (double)p.total;
+        LRN_CUDA(cudaEventRecord(rec.a, st));
+    }
+    const unsigned grid = (unsigned)std::min<long long>(sms, p.total);
+    panel_rotate_kernel<<<grid, 288, PR_SMEM, st>>>(p);
+    LRN_CHECK_LAUNCH();
+    if (prof) {
+        LRN_CUDA(cudaEventRecord(rec.b, st));
+        g_prof.push_back(rec);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 void gemm_set_bulk(bool on) { g_bulk_enabled = on; }
 

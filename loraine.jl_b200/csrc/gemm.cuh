@@ -56,6 +56,20 @@ inline void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const dou
 long long gemm_launch_count();
 // enable / disable the TMA (cp.async.bulk) fed kernel for large A*B^T products (default on; tests compare both paths)
 void gemm_set_bulk(bool on);
+
+// Block-Jacobi panel rotation (see panel_rotate_kernel): cur / nxt are column-major work buffers with leading dimension
+// ldw >= 128 * tiles whose padding rows are zero; pair z owns columns [64 z, 64 z + 64) of cur and its rotated halves go
+// to the 32-column slots slotmap[2z], slotmap[2z+1] of nxt.  rot holds the 64 x 64 rotations (ld 64) one after the other.
+struct PanelRotateParams {
+    const double* cur = nullptr;
+    double* nxt = nullptr;
+    const double* rot = nullptr;
+    const int* slotmap = nullptr;
+    int ldw = 0;
+    int tiles = 0;            // 128-row tiles per panel
+    long long total = 0;      // pairs * tiles
+};
+void panel_rotate(const PanelRotateParams& p, cudaStream_t stream);
 // mode 1: start recording one CUDA-event pair per GEMM launch; mode 0: stop, synchronise and report the totals
 void gemm_profile(int mode, double* ms, double* flops, long long* launches);
 

@@ -163,6 +163,26 @@ def test_block_jacobi_svd(L, m, cond):
     assert 1 <= sweeps.value <= 25
 
 
+@pytest.mark.parametrize("m", [300, 1030, 2100])
+def test_block_jacobi_svd_without_v(L, m):
+    """The solver never accumulates V (G comes from triangular solves); m >= 1024 runs the TMA panel-rotation kernel and
+    the recycled diagonal Gram blocks."""
+    rng = np.random.default_rng(m)
+    U0, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    V0, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    sv = np.linspace(1.0, 5.0, m)[::-1]
+    A = (U0 * sv[None, :]) @ V0.T
+    UD, sg = F(np.zeros((m, m))), np.zeros(m)
+    sweeps, ms = C.c_int32(0), C.c_double(0)
+    assert L.lrn_dbg_svd(m, dp(F(A)), dp(UD), None, dp(sg), 1e-10, C.byref(sweeps), C.byref(ms)) == 0
+    assert np.max(np.abs(sg - sv) / sv) <= 1e-12
+    Un = UD / sg[None, :]
+    assert np.linalg.norm(Un.T @ Un - np.eye(m)) <= 1e-9 * m
+    # A = U D V' with orthogonal V  <=>  A A' = (UD)(UD)'
+    assert np.linalg.norm(A @ A.T - UD @ UD.T) <= 1e-12 * np.linalg.norm(A) ** 2
+    assert 1 <= sweeps.value <= 25
+
+
 @pytest.mark.parametrize("m", [10, 64, 100, 500, 1200])
 def test_lanczos_extremes(L, m):
     rng = np.random.default_rng(m)
