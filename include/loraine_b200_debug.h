@@ -8,7 +8,8 @@
 extern "C" {
 #endif
 
-/* C = alpha*op(A)*op(B)[.*colscale] + beta*C (mode 0) or C = beta*C + alpha*(op(A)op(B)).^2 (mode 1); lower != 0 computes
+/* C = alpha*op(A)*op(B)[.*colscale] + beta*C (mode 0) or C = beta*C + alpha*(op(A)op(B)).^2 (mode 1); mode | 2: the caller
+ * promises op(A)(i,k) = 0 for k < i and op(B)(k,j) = 0 for k < j (tiles skip that part of the K loop); lower != 0 computes
  * only tiles that intersect the lower triangle.  misalign != 0 offsets the device buffers by 8 bytes (exercises the
  * unaligned cp.async path).  reps > 0: the kernel is timed over `reps` launches (CUDA events) into *ms_per_launch. */
 int32_t lrn_dbg_gemm(int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, double alpha, const double* A,

@@ -88,7 +88,7 @@ int32_t lrn_dbg_gemm(int32_t M, int32_t N, int32_t K, int32_t transA, int32_t tr
         if (colscale) cs.upload(colscale, N);
         GemmParams p;
         p.A = dA.p; p.B = dB.p; p.C = dC.p; p.M = M; p.N = N; p.K = K; p.lda = dA.ld; p.ldb = dB.ld; p.ldc = dC.ld;
-        p.transA = transA != 0; p.transB = transB != 0; p.alpha = alpha; p.beta = beta; p.mode = mode; p.lower = lower;
+        p.transA = transA != 0; p.transB = transB != 0; p.alpha = alpha; p.beta = beta; p.mode = mode & 1; p.ktri = (mode & 2) ? 1 : 0; p.lower = lower;
         p.colscale = colscale ? cs.p : nullptr;
         cudaStream_t st = 0;
         gemm(p, st);
@@ -98,7 +98,7 @@ int32_t lrn_dbg_gemm(int32_t M, int32_t N, int32_t K, int32_t transA, int32_t tr
             cudaEvent_t e0, e1;
             LRN_CUDA(cudaEventCreate(&e0)); LRN_CUDA(cudaEventCreate(&e1));
             GemmParams q = p;
-            if (beta != 0.0 && mode == 0) q.beta = 0.0;       // keep magnitudes bounded over repetitions
+            if (beta != 0.0 && (mode & 1) == 0) q.beta = 0.0;       // keep magnitudes bounded over repetitions
             for (int w = 0; w < 3; w++) gemm(q, st);
             LRN_CUDA(cudaEventRecord(e0, st));
             for (int r = 0; r < reps; r++) gemm(q, st);

@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
         for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int KT = (Kz + BK - 1) / BK;
+    const int kt0 = p.ktri ? max(m0, n0) / BK : 0;
     auto issue = [&](int kt) {
-        double* sA = smem + (size_t)(kt % STAGES) * SM::STAGE_ELEMS;
+        double* sA = smem + (size_t)((kt - kt0) % STAGES) * SM::STAGE_ELEMS;
         double* sB = sA + SM::A_ELEMS;
         // op(A) is M x K: !TA -> contiguous along M; TA -> contiguous along K
         load_tile<BM, BK, NT, !TA, ALIGN16>(sA, A, p.lda, m0, kt * BK, p.M, Kz, tid);
@@ -138,15 +139,15 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-        if (s < KT) issue(s);
+        if (kt0 + s < KT) issue(kt0 + s);
         cp_async_commit();
     }
-    for (int kt = 0; kt < KT; kt++) {
+    for (int kt = kt0; kt < KT; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         if (kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
         cp_async_commit();
-        const double* sA = smem + (size_t)(kt % STAGES) * SM::STAGE_ELEMS;
+        const double* sA = smem + (size_t)((kt - kt0) % STAGES) * SM::STAGE_ELEMS;
         const double* sB = sA + SM::A_ELEMS;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
@@ -438,7 +439,7 @@ void launch_cfg(const GemmParams& p, cudaStream_t st) {
         LRN_CUDA(cudaEventCreate(&rec.a));
         LRN_CUDA(cudaEventCreate(&rec.b));
         double kk = (p.K_last > 0 && p.batch2 > 1) ? ((double)p.K * (p.batch2 - 1) + p.K_last) / p.batch2 : (double)p.K;
-        rec.flops = 2.0 * p.M * (double)p.N * kk * p.batch * p.batch2 * (p.lower ? 0.5 : 1.0);
+        rec.flops = 2.0 * p.M * (double)p.N * kk * p.batch * p.batch2 * (p.lower ? 0.5 : 1.0) * (p.ktri ? 1.0 / 3.0 : 1.0);
         LRN_CUDA(cudaEventRecord(rec.a, st));
     }
     kern<<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(p);
@@ -549,7 +550,7 @@ void gemm_set_bulk(bool on) { g_bulk_enabled = on; }
 void gemm(const GemmParams& p, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
     // TMA (bulk copy) path: large A B^T products with 16-byte aligned MN-major operands and K % 32 == 0
-    if (g_bulk_enabled && !p.transA && p.transB && p.batch == 1 && p.batch2 == 1 && !p.colscale && !p.cblkmap && p.K >= 64 &&
+    if (g_bulk_enabled && !p.ktri && !p.transA && p.transB && p.batch == 1 && p.batch2 == 1 && !p.colscale && !p.cblkmap && p.K >= 64 &&
         p.K % 32 == 0 && p.M >= 1024 && p.N >= 1024 && p.row0 == 0 && p.col0 == 0 &&
         ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && p.lda % 2 == 0 && p.ldb % 2 == 0) {
         const int Mf = p.M / 128 * 128, Nf = p.N / 128 * 128;

@@ -30,6 +30,8 @@ struct GemmParams {
     const int* cblkmap = nullptr;
     // global offsets of the sub-problem (only used by the lower-triangle tile test when a product is split into regions)
     int row0 = 0, col0 = 0;
+    int ktri = 0;             // 1: op(A) (M x K) and op(B) (K x N) vanish for k < row resp. k < column (product of a transposed
+                              // lower-triangular factor with a lower-triangular factor): tiles start their K loop at max(m0, n0)
 };
 
 // Enqueue on `stream`. Never synchronises.

@@ -562,6 +562,16 @@ int32_t lrn_get_slack(lrn_handle_t h, double* const* S, double* s_lin) {
     });
 }
 
+// symmetric m x m product op(A) op(B): only the tiles that meet the lower triangle are computed, then mirrored
+static void gemm_sym(cudaStream_t st, bool ta, bool tb, int m, const double* A, int lda, const double* B, int ldb, double* C,
+                     int ldc) {
+    GemmParams p;
+    p.A = A; p.B = B; p.C = C; p.M = m; p.N = m; p.K = m; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.transA = ta; p.transB = tb; p.lower = 1;
+    gemm(p, st);
+    mat_mirror_lower(st, m, C, ldc);
+}
+
 // ---- hot path -------------------------------------------------------------------------------------------------------
 int32_t lrn_find_mu(lrn_handle_t h, double* mu) {
     return guarded(h, [&]() -> int32_t {
@@ -593,7 +603,12 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             zero_strict_upper(B.LX.p(), m, ld, st);
             zero_strict_upper(B.LS.p(), m, ld, st);
             // CC = L_S' L_X                                                   (src/prepare_W.jl:39)
-            gemm_tn(st, m, m, m, 1.0, B.LS.p(), ld, B.LX.p(), ld, 0.0, B.T1.p(), ld);
+            {
+                GemmParams p;                    // both factors are lower triangular: the K loop of a tile starts at max(m0, n0)
+                p.A = B.LS.p(); p.B = B.LX.p(); p.C = B.T1.p(); p.M = m; p.N = m; p.K = m; p.lda = ld; p.ldb = ld; p.ldc = ld;
+                p.transA = true; p.ktri = 1;
+                gemm(p, st);
+            }
         }
         // U*D, D = svd(CC) without accumulating V                                (src/prepare_W.jl:42)
         {
@@ -617,12 +632,10 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             // Gi = inv(G) (src/prepare_W.jl:63) is never multiplied with anything on the device (find_step uses the closed
             // forms of the scaled directions); it is produced on demand for the LRN_ARR_GI parity hook from U D kept in T2.
             // W = G G'                                                        (src/prepare_W.jl:64)
-            gemm_nt(st, m, m, m, 1.0, B.G.p(), ld, B.G.p(), ld, 0.0, B.W.p(), ld);
-            mat_symmetrize(st, m, B.W.p(), ld);
+            gemm_sym(st, false, true, m, B.G.p(), ld, B.G.p(), ld, B.W.p(), ld);
             // Si = S^{-1} = (G D^{-1/2}) (G D^{-1/2})'                        (src/prepare_W.jl:68; G'SG = D)
             mat_scale_cols(st, m, m, B.T1.p(), ld, B.G.p(), ld, B.dm12.p);
-            gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.T1.p(), ld, 0.0, B.Si.p(), ld);
-            mat_symmetrize(st, m, B.Si.p(), ld);
+            gemm_sym(st, false, true, m, B.T1.p(), ld, B.T1.p(), ld, B.Si.p(), ld);
             // DDsi = 1 ./ sqrt(diag(G' S G))  (src/prepare_W.jl:71-74).  With G = L_S^{-T} (U D) D^{-1/2} the p-th diagonal entry
             // of G' S G is ||(U D)(:,p)||^2 / D_p = D_p exactly (D_p IS that column norm), so DDsi = D^{-1/2} without a GEMM.
             LRN_CUDA(cudaMemcpyAsync(B.DDsi.p, B.dm12.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -728,7 +741,7 @@ int32_t lrn_rhs_predictor(lrn_handle_t h) {
             // h += AA * vec(W (Rd + S) W)                                     (src/makeBBBB.jl:225)
             mat_lincomb(st, m, m, B.T1.p(), ld, 1.0, B.Rd.p(), ld, 1.0, B.S.p(), ld, 0.0, nullptr, 0);
             gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
-            gemm_nn(st, m, m, m, 1.0, B.T2.p(), ld, B.W.p(), ld, 0.0, B.T3.p(), ld);
+            gemm_sym(st, false, false, m, B.T2.p(), ld, B.W.p(), ld, B.T3.p(), ld);
             sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
         }
         add_lp_rhs(h, 0, 0.0);
@@ -747,10 +760,10 @@ int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
             const int m = B.m, ld = B.ld;
             // h += AA * vec(G (G' Rd G + diag(D) - diag(sigma mu ./ D) - RNT) G')      (src/predictor_corrector.jl:186)
             gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_tn(st, m, m, m, 1.0, B.G.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+            gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
             mat_corr_inner(st, m, B.T2.p(), ld, B.D.p, sm, B.RNT.p(), ld);
             gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.T2.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.G.p(), ld, 0.0, B.T3.p(), ld);
+            gemm_sym(st, false, true, m, B.T1.p(), ld, B.G.p(), ld, B.T3.p(), ld);
             sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
         }
         add_lp_rhs(h, 1, sm);
@@ -817,14 +830,14 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
             sp_scatter_ATy(st, B.sp, h->dely.p, -1.0, B.dS.p(), ld);
             // delSb = G' delS G                                                (:263)
             gemm_nn(st, m, m, m, 1.0, B.dS.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_tn(st, m, m, m, 1.0, B.G.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+            gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
             // delX = mat(-X - W delS W)                         (predictor, :255)
             //      = mat(sigma mu Si - X - W delS W + G RNT G') (corrector, :257)
             // with W = G G' both congruences collapse into ONE:  delX = mat([sigma mu Si] - X + G (RNT - delSb) G')
             if (predict) mat_lincomb(st, m, m, B.T3.p(), ld, -1.0, B.T2.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
             else mat_lincomb(st, m, m, B.T3.p(), ld, -1.0, B.T2.p(), ld, 1.0, B.RNT.p(), ld, 0.0, nullptr, 0);
             gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.T3.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_nt(st, m, m, m, 1.0, B.T1.p(), ld, B.G.p(), ld, 0.0, B.T4.p(), ld);
+            gemm_sym(st, false, true, m, B.T1.p(), ld, B.G.p(), ld, B.T4.p(), ld);
             if (predict)
                 mat_sym_lincomb(st, m, B.dX.p(), ld, -1.0, B.X.p(), ld, 1.0, B.T4.p(), ld, 0.0, nullptr, 0, 0.0, nullptr, 0);
             else

@@ -163,6 +163,18 @@ def test_block_jacobi_svd(L, m, cond):
     assert 1 <= sweeps.value <= 25
 
 
+@pytest.mark.parametrize("m", [5, 64, 257, 700, 1500])
+def test_gemm_triangular_operands(L, m):
+    """CC = L_S' L_X (src/prepare_W.jl:39): both factors lower triangular, tiles start their K loop at max(m0, n0)."""
+    rng = np.random.default_rng(m)
+    LS = np.tril(rng.standard_normal((m, m)))
+    LX = np.tril(rng.standard_normal((m, m)))
+    Cm = F(np.zeros((m, m)))
+    assert L.lrn_dbg_gemm(m, m, m, 1, 0, 1.0, dp(F(LS)), dp(F(LX)), 0.0, dp(Cm), 2, 0, None, 0, 0, None) == 0
+    ref = LS.T @ LX
+    assert np.max(np.abs(Cm - ref)) <= 1e-13 * m * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("m", [300, 1030, 2100])
 def test_block_jacobi_svd_without_v(L, m):
     """The solver never accumulates V (G comes from triangular solves); m >= 1024 runs the TMA panel-rotation kernel and
