@@ -45,9 +45,9 @@ typedef struct lrn_options {
     int32_t datasparsity;   /* kappa of prep_sparse! (src/model.jl:153-174); only used when schur_split = 1 */
     int32_t schur_split;    /* 0 = cost model picks F1/F3 per matrix (default), 1 = reference rule nnz > kappa -> F1 */
     int32_t rank1_mode;     /* 0 = SpMM + DMMA SYRK with squared epilogue (reference formulation) */
-    double svd_tol;         /* block-Jacobi stopping level of max |u_i.u_j|/(|u_i||u_j|) over the rotated columns (0 -> default 1e-8): measured
-                             * at the start of every sweep and, for blocks with m >= 1024 in the quadratic regime, exactly after the sweep
-                             * (Gram product), which saves the final verification sweep */
+    double svd_tol;         /* block-Jacobi stopping level of max |u_i.u_j|/(|u_i||u_j|) over the rotated columns (0 -> default 1e-8), measured
+                             * at the START of the last sweep (quadratic convergence: ~1e-14 after it).  Blocks with m >= 1024 may stop one
+                             * sweep earlier when a Gram product shows the columns are already orthogonal to 1e4 svd_tol^2 */
     double lanczos_tol;     /* relative Ritz residual for lambda_min (0 -> default 1e-8) */
     int32_t device;         /* CUDA device ordinal, -1 = current / LOCAL_RANK */
     int32_t reserved;

@@ -84,6 +84,7 @@ struct LanczosWork {
     DevBuf<double> Q;            // m x (kmax+1)
     DevBuf<double> w, c;         // m, kmax+1
     DevBuf<double> scal;         // small device scalars
+    DevBuf<double> ab;           // 2 * kmax: Lanczos alpha_j, beta_j (read back at the check points only)
     double* h_scal = nullptr;    // pinned host mirror
     DevBuf<double> S;            // kmax x nev Ritz coefficient upload
     void ensure(int m_, int kmax_);
