@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--cpu-sample-n", type=int, default=2000, help="side of the reduced instance timed on the host CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solve", action="store_true", help="skip the end-to-end solve to convergence reported under `solve`")
     return ap.parse_args()
 
 
@@ -277,6 +278,16 @@ def run_b200(args):
     L.lrn_dbg_gemm_profile(0, C.byref(ms), C.byref(fl), C.byref(nl))
     peak = C.c_double()
     L.lrn_dbg_peak(0, C.byref(peak))
+    # ---- end-to-end solve to the reference's stopping rule (outside the timed regions; every rank runs it) ---------------
+    solve_info = None
+    if not args.no_solve:
+        barrier()
+        t0 = time.perf_counter()
+        S.solve(s, ha)
+        barrier()
+        solve_info = dict(seconds=time.perf_counter() - t0, iterations=int(s.iter), status=int(s.status),
+                          dimacs_error=float(s.DIMACS_error), primal_obj=float(s.primal_obj), dual_obj=float(s.dual_obj),
+                          cg_iterations=int(s.cg_iter_tot) if s.kit == 1 else None)
 
     tmax = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -305,6 +316,7 @@ def run_b200(args):
         e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=e2e_steps),
         gpu_launches=int(launches),
         clocks=clocks,
+        solve=solve_info,
         phases_ms_per_iteration={k: v[0] / args.steps for k, v in phase.items()},
         schur=dict(assemble_ms=asm_ms, assemble_tflops=alg["assemble"] / (asm_ms * 1e-3) / 1e12 if asm_ms > 0 else None,
                    factor_ms=fac_ms, factor_tflops=alg["factor"] / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else None,

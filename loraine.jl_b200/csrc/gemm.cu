@@ -319,63 +319,51 @@ __global__ void __launch_bounds__(288) dgemm_dmma_bulk_nt_kernel(const GemmParam
 // slots the round-robin ordering assigns them in the next round.  Rows are padded to whole tiles (zero rows stay zero).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int PR_LDA = 128 + 4, PR_LDJ = 64 + 4, PR_ST = 2;
-constexpr int PR_A_ELEMS = 64 * PR_LDA, PR_J_ELEMS = 64 * PR_LDJ;
-constexpr size_t PR_SMEM = (size_t)(PR_ST * PR_A_ELEMS + PR_J_ELEMS) * sizeof(double) + 64;
+constexpr int PR_A_ELEMS = 64 * PR_LDA, PR_J_ELEMS = 64 * PR_LDJ, PR_STAGE_ELEMS = PR_A_ELEMS + PR_J_ELEMS;
+constexpr size_t PR_SMEM = (size_t)PR_ST * PR_STAGE_ELEMS * sizeof(double) + 64;
 
 __global__ void __launch_bounds__(288) panel_rotate_kernel(const PanelRotateParams p) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t sJ_addr = sbase + (uint32_t)(PR_ST * PR_A_ELEMS * sizeof(double));
-    const uint32_t bars = sJ_addr + (uint32_t)(PR_J_ELEMS * sizeof(double));
-    const uint32_t jfull = bars + 8 * (2 * PR_ST), jempty = jfull + 8;     // full[s] = bars + 8 s, empty[s] = bars + 8 (ST + s)
+    const uint32_t bars = sbase + (uint32_t)(PR_ST * PR_STAGE_ELEMS * sizeof(double));   // full[s] = bars + 8 s, empty[s] after them
     if (tid == 0) {
         for (int s = 0; s < PR_ST; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (PR_ST + s), 8); }
-        mbar_init(jfull, 1);
-        mbar_init(jempty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const long long t0 = (long long)blockIdx.x * p.total / gridDim.x, t1 = (long long)(blockIdx.x + 1) * p.total / gridDim.x;
+    // tasks are dealt round-robin (task t -> CTA t mod grid); every stage carries its own copy of the pair's rotation, so a
+    // CTA may move from pair to pair freely (the 32 KB rotations come from L2).  Walking the pairs in opposite directions in
+    // consecutive kernels to catch the tail of the 200 MB work matrix in L2 was measured: no gain (within 1 %).
+    const long long G = gridDim.x;
     if (warp == 8) {
-        int prevz = -1, jl = 0, i = 0;
-        for (long long t = t0; t < t1; t++, i++) {
+        int i = 0;
+        for (long long t = blockIdx.x; t < p.total; t += G, i++) {
             const int z = (int)(t / p.tiles), tile = (int)(t - (long long)z * p.tiles);
-            if (z != prevz) {
-                mbar_wait(jempty, (jl & 1) ^ 1);
-                if (lane == 0) mbar_expect_tx(jfull, 64u * 64u * 8u);
-                __syncwarp();
-                const double* Jg = p.rot + (size_t)z * 4096;
-                for (int l = lane; l < 64; l += 32)
-                    bulk_g2s(sJ_addr + (uint32_t)(l * PR_LDJ * sizeof(double)), Jg + l * 64, 64u * 8u, jfull);
-                jl++;
-                prevz = z;
-            }
             const int s = i % PR_ST;
             mbar_wait(bars + 8 * (PR_ST + s), ((i / PR_ST) & 1) ^ 1);
-            if (lane == 0) mbar_expect_tx(bars + 8 * s, 64u * 128u * 8u);
+            if (lane == 0) mbar_expect_tx(bars + 8 * s, 64u * 128u * 8u + 64u * 64u * 8u);
             __syncwarp();
             const double* Ag = p.cur + (size_t)z * 64 * p.ldw + (size_t)tile * 128;
-            const uint32_t sa = sbase + (uint32_t)(s * PR_A_ELEMS * sizeof(double));
-            for (int l = lane; l < 64; l += 32)
+            const double* Jg = p.rot + (size_t)z * 4096;
+            const uint32_t sa = sbase + (uint32_t)(s * PR_STAGE_ELEMS * sizeof(double));
+            const uint32_t sj = sa + (uint32_t)(PR_A_ELEMS * sizeof(double));
+            for (int l = lane; l < 64; l += 32) {
                 bulk_g2s(sa + (uint32_t)(l * PR_LDA * sizeof(double)), Ag + (size_t)l * p.ldw, 128u * 8u, bars + 8 * s);
+                bulk_g2s(sj + (uint32_t)(l * PR_LDJ * sizeof(double)), Jg + l * 64, 64u * 8u, bars + 8 * s);
+            }
         }
         return;
     }
     const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;
     const int lr = lane >> 2, lk = lane & 3;
-    const double* sJ = smem + PR_ST * PR_A_ELEMS;
-    int prevz = -1, jl = 0, i = 0;
-    for (long long t = t0; t < t1; t++, i++) {
+    int i = 0;
+    for (long long t = blockIdx.x; t < p.total; t += G, i++) {
         const int z = (int)(t / p.tiles), tile = (int)(t - (long long)z * p.tiles);
-        if (z != prevz) {
-            mbar_wait(jfull, jl & 1);
-            jl++;
-            prevz = z;
-        }
         const int s = i % PR_ST;
         mbar_wait(bars + 8 * s, (i / PR_ST) & 1);
-        const double* sA = smem + (size_t)s * PR_A_ELEMS;
+        const double* sA = smem + (size_t)s * PR_STAGE_ELEMS;
+        const double* sJ = sA + PR_A_ELEMS;
         double acc[4][4][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -394,10 +382,7 @@ __global__ void __launch_bounds__(288) panel_rotate_kernel(const PanelRotatePara
                 for (int b_ = 0; b_ < 4; b_++) dmma884(acc[a_][b_][0], acc[a_][b_][1], a[a_], b[b_]);
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(bars + 8 * (PR_ST + s));
-            if (t + 1 == t1 || (int)((t + 1) / p.tiles) != z) mbar_arrive(jempty);
-        }
+        if (lane == 0) mbar_arrive(bars + 8 * (PR_ST + s));
         // both 32-column halves of the pair go to their own slot of the next arrangement
         const int slot = p.slotmap[2 * z + (warp & 1)];
         double* Cz = p.nxt + (size_t)slot * 32 * p.ldw + (size_t)tile * 128 + wm0 + lr;
