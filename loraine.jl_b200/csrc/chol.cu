@@ -400,6 +400,149 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Triangular solves with 256-wide steps.  After a factorisation the inverses of the 256 x 256 diagonal blocks of L are
+// built once (chol_build_tinv: block forward substitution on the stored 64 x 64 inverses, batched DMMA GEMMs over all
+// blocks), so a step is two launches: y_b = inv(L_bb) x_b (one CTA, 1024 threads, 256 KB from L2/HBM) and the update of the
+// remaining right-hand side with the (n - j) x 256 panel (forward: 64 rows x 4 column quarters per CTA, 16 loads in flight
+// per thread; backward: one column of L per warp pass, coalesced along the column).  L is read once per direction.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SW = 256;
+
+__global__ void tinv_diag_kernel(const double* __restrict__ dinv, double* __restrict__ X, int nsb_total) {
+    // X block b = sb / 4, sub-block i = sb % 4: X_ii = D_i (lower triangle)
+    const int sb = blockIdx.x;
+    if (sb >= nsb_total) return;
+    const double* d = dinv + (size_t)sb * DB * DB;
+    double* x = X + (size_t)(sb / 4) * SW * SW + (size_t)(sb % 4) * DB * SW + (sb % 4) * DB;
+    for (int idx = threadIdx.x; idx < DB * DB; idx += blockDim.x) {
+        const int r = idx & 63, c = idx >> 6;
+        x[r + (size_t)c * SW] = (r >= c) ? d[idx] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+    trsv_diag_kernel(const double* __restrict__ X, int jb, const double* __restrict__ rhs, double* __restrict__ sol, int dir,
+                     const double* __restrict__ Xnext) {
+    __shared__ double xs[SW], red[4][SW];
+    const int tid = threadIdx.x;
+    if (tid < SW) xs[tid] = (tid < jb) ? rhs[tid] : 0.0;
+    if (Xnext) {   // pull the next step's inverse block (512 KB) towards L2 while this step runs
+        const char* pn = reinterpret_cast<const char*>(Xnext) + (size_t)tid * 512;
+#pragma unroll
+        for (int u = 0; u < 4; u++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + u * 128));
+    }
+    __syncthreads();
+    if (!dir) {
+        // y_r = sum_{c <= r} X(r, c) x_c : thread (r, part) takes the columns c = part (mod 4), 16 loads in flight
+        const int r = tid & 255, part = tid >> 8;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (r < jb) {
+            const double* Xr = X + r;
+#pragma unroll 1
+            for (int t0 = 0; t0 < 64; t0 += 16) {
+                if (part + 4 * t0 > r) break;
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const int c = part + 4 * (t0 + u);
+                    v[u] = (c <= r) ? Xr[(size_t)c * SW] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    a0 += v[u] * xs[part + 4 * (t0 + u)];
+                    a1 += v[u + 1] * xs[part + 4 * (t0 + u + 1)];
+                    a2 += v[u + 2] * xs[part + 4 * (t0 + u + 2)];
+                    a3 += v[u + 3] * xs[part + 4 * (t0 + u + 3)];
+                }
+            }
+        }
+        red[part][r] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (tid < jb) sol[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    } else {
+        // y_r = sum_{c >= r} X(c, r) x_c : one column of X per warp pass, the 8 rows of a warp are loaded together
+        const int lane = tid & 31, warp = tid >> 5;
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = warp + 32 * k;
+            const double* col = X + (size_t)r * SW;
+            double a = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = 32 * u + lane;
+                if (c >= r && c < jb) a += col[c] * xs[c];
+            }
+            acc[k] = a;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double a = warp_sum(acc[k]);
+            const int r = warp + 32 * k;
+            if (lane == 0 && r < jb) sol[r] = a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    trsv_update_fwd_kernel(const double* __restrict__ L, int lda, int n, int j0, int jb, const double* __restrict__ y,
+                           double* __restrict__ rhs) {
+    __shared__ double ys[SW], red[4][64];
+    const int tid = threadIdx.x, r = tid & 63, q = tid >> 6;
+    ys[tid] = (tid < jb) ? y[tid] : 0.0;
+    __syncthreads();
+    const int i = j0 + jb + blockIdx.x * 64 + r;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (i < n) {
+        const int c0 = q * 64, c1 = min(jb, c0 + 64);
+        const double* Lp = L + (size_t)j0 * lda + i;
+        int c = c0;
+        for (; c + 15 < c1; c += 16) {           // 16 independent loads in flight per thread
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = Lp[(size_t)(c + u) * lda];
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+                a0 += v[u] * ys[c + u];
+                a1 += v[u + 1] * ys[c + u + 1];
+                a2 += v[u + 2] * ys[c + u + 2];
+                a3 += v[u + 3] * ys[c + u + 3];
+            }
+        }
+        for (; c < c1; c++) a0 += Lp[(size_t)c * lda] * ys[c];
+    }
+    red[q][r] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (q == 0 && i < n) rhs[i] -= (red[0][r] + red[1][r]) + (red[2][r] + red[3][r]);
+}
+
+__global__ void __launch_bounds__(256)
+    trsv_update_bwd_kernel(const double* __restrict__ L, int lda, int j0, int jb, const double* __restrict__ y,
+                           double* __restrict__ rhs) {
+    __shared__ double ys[SW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ys[tid] = (tid < jb) ? y[tid] : 0.0;
+    __syncthreads();
+    // 32 columns of L per CTA, 4 per warp, two at a time
+    const int ibase = blockIdx.x * 32 + warp * 4;
+    for (int u = 0; u < 4; u += 2) {
+        const int i0 = ibase + u, i1 = i0 + 1;
+        if (i0 >= j0) break;
+        const double* L0 = L + (size_t)i0 * lda + j0;
+        const double* L1 = (i1 < j0) ? L + (size_t)i1 * lda + j0 : L0;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+        for (int c = lane; c < jb; c += 32) { a0 += L0[c] * ys[c]; a1 += L1[c] * ys[c]; }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+            rhs[i0] -= a0;
+            if (i1 < j0) rhs[i1] -= a1;
+        }
+    }
+}
+
 __global__ void zero_upper_kernel(double* A, int n, int lda) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y;
@@ -462,23 +605,66 @@ void chol_lookahead(double* A, int n, int lda, CholWork& work, cudaStream_t st) 
 
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st) {
     work.ensure(n);
+    work.tinv_for = nullptr;
     LRN_CUDA(cudaMemsetAsync(work.info_ptr(), 0, sizeof(int), st));
     if (n <= 0) return;
     if (n >= 1024) chol_lookahead(A, n, lda, work, st);
     else chol_rec(A, n, lda, work.dinv.p, work.info_ptr(), 0, work, st);
 }
 
-void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {
+// inverses of the 256 x 256 diagonal blocks of L: X_ii = D_i, X_ij = -D_i (L[i, j:i] X[j:i, j]) for sub-blocks i > j
+void chol_build_tinv(const double* L, int n, int lda, CholWork& work, cudaStream_t st) {
+    const int nblk = (int)cdiv(n, SW), nfull = n / SW, tail = n - nfull * SW;
+    if (work.tinv.n < (size_t)nblk * SW * SW) work.tinv.alloc((size_t)nblk * SW * SW);
+    if (work.tscr.n < (size_t)nblk * DB * DB) work.tscr.alloc((size_t)nblk * DB * DB);
+    const int nsb_total = (int)cdiv(n, DB);
+    tinv_diag_kernel<<<nsb_total, 256, 0, st>>>(work.dinv.p, work.tinv.p, nsb_total);
+    LRN_CHECK_LAUNCH();
+    for (int grp = 0; grp < 2; grp++) {
+        // group 0: all full blocks in one batch; group 1: the partial last block
+        const int b0 = grp ? nfull : 0, cnt = grp ? (tail > 0 ? 1 : 0) : nfull, jb = grp ? tail : SW;
+        if (cnt <= 0) continue;
+        const int nsb = (int)cdiv(jb, DB);
+        const double* Lb = L + (size_t)b0 * SW * lda + (size_t)b0 * SW;
+        double* Xb = work.tinv.p + (size_t)b0 * SW * SW;
+        const double* Db = work.dinv.p + (size_t)b0 * 4 * DB * DB;
+        for (int j = 0; j + 1 < nsb; j++)
+            for (int i = j + 1; i < nsb; i++) {
+                const int rb = std::min(DB, jb - i * DB), K = DB * (i - j);
+                GemmParams g;                       // S = L[i, j:i] X[j:i, j]
+                g.A = Lb + (size_t)j * DB * lda + i * DB; g.lda = lda; g.sA = (long long)SW * lda + SW;
+                g.B = Xb + (size_t)j * DB * SW + j * DB; g.ldb = SW; g.sB = (long long)SW * SW;
+                g.C = work.tscr.p; g.ldc = DB; g.sC = DB * DB;
+                g.M = rb; g.N = DB; g.K = K; g.batch = cnt;
+                gemm(g, st);
+                GemmParams f;                       // X_ij = -D_i S
+                f.A = Db + (size_t)i * DB * DB; f.lda = DB; f.sA = 4LL * DB * DB;
+                f.B = work.tscr.p; f.ldb = DB; f.sB = DB * DB;
+                f.C = Xb + (size_t)j * DB * SW + i * DB; f.ldc = SW; f.sC = (long long)SW * SW;
+                f.M = rb; f.N = DB; f.K = rb; f.alpha = -1.0; f.batch = cnt;
+                gemm(f, st);
+            }
+    }
+    work.tinv_for = L;
+}
+
+void chol_solve(const double* L, int n, int lda, CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {
     if (n <= 0) return;
-    const int nblk = (int)cdiv(n, DB);
+    if (work.tinv_for != L) chol_build_tinv(L, n, lda, work, st);
+    const int nstep = (int)cdiv(n, SW);
     for (int dir = 0; dir < 2; dir++) {
         if (!(which & (dir ? 2 : 1))) continue;
-        for (int s = 0; s < nblk; s++) {
-            const int b = dir ? nblk - 1 - s : s;
-            const int j0 = b * DB, jb = (n - j0 < DB) ? (n - j0) : DB;
+        for (int s = 0; s < nstep; s++) {
+            const int b = dir ? nstep - 1 - s : s;
+            const int j0 = b * SW, jb = (n - j0 < SW) ? (n - j0) : SW;
+            const int bn = dir ? b - 1 : b + 1;
+            const double* Xn = (bn >= 0 && bn < nstep && (size_t)(bn + 1) * SW * SW <= work.tinv.n) ? work.tinv.p + (size_t)bn * SW * SW : nullptr;
+            trsv_diag_kernel<<<1, 1024, 0, st>>>(work.tinv.p + (size_t)b * SW * SW, jb, x + j0, tmp + j0, dir, Xn);
+            LRN_CHECK_LAUNCH();
             const int rest = dir ? j0 : n - j0 - jb;
-            const int grid = rest > 0 ? (int)cdiv(rest, 256) : 1;
-            trsv_step_kernel<<<grid, 256, 0, st>>>(L, lda, n, j0, jb, work.dinv.p + (size_t)b * DB * DB, x, tmp, dir);
+            if (rest <= 0) continue;
+            if (!dir) trsv_update_fwd_kernel<<<(unsigned)cdiv(rest, 64), 256, 0, st>>>(L, lda, n, j0, jb, tmp + j0, x);
+            else trsv_update_bwd_kernel<<<(unsigned)cdiv(rest, 32), 256, 0, st>>>(L, lda, j0, jb, tmp + j0, x);
             LRN_CHECK_LAUNCH();
         }
         LRN_CUDA(cudaMemcpyAsync(x, tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));

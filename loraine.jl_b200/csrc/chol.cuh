@@ -15,6 +15,8 @@ struct CholWork {
     int* info_ext = nullptr;  // optional external flag location (lets the caller gather many flags with one copy)
     DevBuf<double> xinv;      // inverse of the current panel's diagonal block (kb x kb) + 64 x kb scratch
     DevBuf<double> pout;      // out-of-place panel solve result (rows x kb)
+    DevBuf<double> tinv, tscr; // inverses of the 256 x 256 diagonal blocks of L (triangular solves) + 64 x 64 scratch per block
+    const double* tinv_for = nullptr;   // factor the inverses belong to (reset by every factorisation)
     cudaStream_t aux = nullptr;   // high-priority side stream (panel factorisation + broadcast look-ahead in multi-GPU runs)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n = 0;
@@ -39,8 +41,9 @@ void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int*
 // creates the high-priority side stream and the events of `work` on first use
 void ensure_aux(CholWork& work);
 
-// x <- L^{-1} x (which=1), x <- L^{-T} x (which=2), both (which=3). `tmp` has n doubles. Uses work.dinv of the same factor.
-void chol_solve(const double* L, int n, int lda, const CholWork& work, double* x, double* tmp, int which, cudaStream_t st);
+// x <- L^{-1} x (which=1), x <- L^{-T} x (which=2), both (which=3). `tmp` has n doubles. Uses work.dinv of the same factor;
+// the first solve after a factorisation builds the inverses of the 256 x 256 diagonal blocks (work.tinv).
+void chol_solve(const double* L, int n, int lda, CholWork& work, double* x, double* tmp, int which, cudaStream_t st);
 
 // Y <- L^{-T} Y for an n x ncols right-hand-side block (in place), blocked with the inverted diagonal blocks of `work`:
 // used for G = L_S^{-T} (U D^{1/2}) in the NT scaling (no accumulated right singular vectors needed).

@@ -46,6 +46,7 @@ void dist_allreduce_sum(double* buf, size_t count, DistCtx& ctx, cudaStream_t st
 }
 
 void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int pw, DevBuf<double>& panelbuf, cudaStream_t st) {
+    work.tinv_for = nullptr;   // the triangular solves rebuild their diagonal-block inverses from the new factor
     work.ensure(n);
     LRN_REQUIRE(pw % CHOL_DB == 0, "panel width must be a multiple of 64");
     const int npan = (int)cdiv(n, pw), ldp = pad_ld(n);
