@@ -23,10 +23,12 @@ L.lrn_dbg_gemm.argtypes = [i32, i32, i32, i32, i32, dbl, pd, pd, dbl, pd, i32, i
 dp = lambda a: a.ctypes.data_as(pd)
 rng = np.random.default_rng(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
-A = np.asfortranarray(rng.standard_normal((n, n)))
+Kp = (n + 31) // 32 * 32          # the solver zero-pads B*G to K % 32 == 0: TMA-fed kernel + edge strips
+A = np.asfortranarray(np.zeros((n, Kp)))
+A[:, :n] = rng.standard_normal((n, n))
 H = np.asfortranarray(np.zeros((n, n)))
 ms = C.c_double()
-L.lrn_dbg_gemm(n, n, n, 0, 1, 1.0, dp(A), dp(A), 1.0, dp(H), 1, 1, None, 0, 3, C.byref(ms))
+L.lrn_dbg_gemm(n, n, Kp, 0, 1, 1.0, dp(A), dp(A), 1.0, dp(H), 1, 1, None, 0, 3, C.byref(ms))
 print("syrk-square lower %d: %.3f ms  %.2f TFLOP/s (algorithmic n^3)" % (n, ms.value, n ** 3 / (ms.value * 1e-3) / 1e12))
 P = np.asfortranarray(rng.standard_normal((n, 256)))
 L.lrn_dbg_gemm(n, n, 256, 0, 1, -1.0, dp(P), dp(P), 1.0, dp(H), 0, 1, None, 0, 3, C.byref(ms))
