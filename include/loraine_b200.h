@@ -153,7 +153,8 @@ int32_t lrn_timers(lrn_handle_t h, double* ms, int64_t* calls, int32_t reset);
 /* number of kernels launched by the library through this handle's process so far */
 int64_t lrn_kernel_launches(void);
 /* change an option after creation (the reference mutates solver.aamat / solver.preconditioner in the hybrid switch,
- * src/Solvers.jl:339-347): name in {"aamat", "erank", "svd_tol", "lanczos_tol"} */
+ * src/Solvers.jl:339-347): name in {"aamat", "erank", "svd_tol", "lanczos_tol", "sparse_op"}; sparse_op: 0 = dense W M W form of the
+ * kit = 1 Schur operator, 1 = sparse-aware form wherever the data is stored symmetrically, -1 = automatic (default) */
 int32_t lrn_set_option(lrn_handle_t h, const char* name, double value);
 /* diagnostic counters of the last calls: [0] svd sweeps, [1] lanczos iterations (sum), [2] lanczos not converged count */
 int32_t lrn_stats(lrn_handle_t h, int64_t* out3);

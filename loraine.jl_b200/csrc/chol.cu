@@ -355,51 +355,6 @@ void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, Chol
     }
 }
 
-// One launch per 64-column step (a cooperative single-launch variant with grid-wide barriers measured SLOWER on B200:
-// 25 us per step against ~5 us here).  Every CTA stages inv(L_jj) in shared memory and recomputes y_j = inv(L_jj) x_j
-// itself, then updates its slice of the remaining right-hand side; L is read exactly once per direction (HBM-bound).
-__global__ void __launch_bounds__(256)
-    trsv_step_kernel(const double* __restrict__ L, int lda, int n, int j0, int jb, const double* __restrict__ dj,
-                     double* __restrict__ rhs, double* __restrict__ sol, int dir) {
-    __shared__ double xj[DB], yj[DB], sd[DB * (DB + 1)];
-    const int tid = threadIdx.x;
-    if (tid < jb) xj[tid] = rhs[j0 + tid];
-    for (int idx = tid; idx < DB * DB; idx += 256) {           // inv(L_jj) (or its transpose) -> shared, row-major, padded
-        const int r = idx & 63, c = idx >> 6;                   // dinv(r,c) at r + c*64
-        if (!dir) sd[r * (DB + 1) + c] = dj[idx];
-        else sd[c * (DB + 1) + r] = dj[idx];
-    }
-    __syncthreads();
-    if (tid < jb) {
-        double acc = 0.0;
-        const double* row = sd + tid * (DB + 1);
-#pragma unroll 8
-        for (int c = 0; c < jb; c++) acc += row[c] * xj[c];     // zero entries outside the triangle contribute nothing
-        yj[tid] = acc;
-        if (blockIdx.x == 0) sol[j0 + tid] = acc;
-    }
-    __syncthreads();
-    if (!dir) {
-        const int i = j0 + jb + blockIdx.x * 256 + tid;
-        if (i < n) {
-            const double* Lp = L + (size_t)j0 * lda + i;
-            double acc = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < jb; c++) acc += Lp[(size_t)c * lda] * yj[c];
-            rhs[i] -= acc;
-        }
-    } else {
-        const int i = blockIdx.x * 256 + tid;
-        if (i < j0) {
-            const double* Lp = L + (size_t)i * lda + j0;
-            double acc = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < jb; c++) acc += Lp[c] * yj[c];
-            rhs[i] -= acc;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Triangular solves with 256-wide steps.  After a factorisation the inverses of the 256 x 256 diagonal blocks of L are
 // built once (chol_build_tinv: block forward substitution on the stored 64 x 64 inverses, batched DMMA GEMMs over all

@@ -576,15 +576,6 @@ __global__ void __launch_bounds__(128) gemv_n_sub_split_kernel(const double* __r
     for (; k < cols; k++) s0 += Q[(size_t)k * ld + i] * cs_[k];
     w[i] -= (s0 + s1) + (s2 + s3);
 }
-// w[i] -= sum_k Q[i + k*ld] * c[k]
-__global__ void __launch_bounds__(256) gemv_n_sub_kernel(const double* __restrict__ Q, int ld, int rows, int cols,
-                                                         const double* __restrict__ c, double* __restrict__ w) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    double s = 0.0;
-    for (int k = 0; k < cols; k++) s += Q[(size_t)k * ld + i] * c[k];
-    w[i] -= s;
-}
 __global__ void __launch_bounds__(1024) lanczos_init_kernel(double* __restrict__ q, int m) {
     __shared__ double red[32];
     double s = 0.0;

@@ -568,6 +568,8 @@ void gemm(const GemmParams& p, cudaStream_t stream) {
 
 long long gemm_launch_count() { return g_launches.load(); }
 
+bool gemm_profile_active() { return g_prof_on; }
+
 void gemm_profile(int mode, double* ms, double* flops, long long* launches) {
     if (mode == 1) {
         for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -74,5 +74,6 @@ struct PanelRotateParams {
 void panel_rotate(const PanelRotateParams& p, cudaStream_t stream);
 // mode 1: start recording one CUDA-event pair per GEMM launch; mode 0: stop, synchronise and report the totals
 void gemm_profile(int mode, double* ms, double* flops, long long* launches);
+bool gemm_profile_active();   // per-launch event timing is on (stream capture must not be used meanwhile)
 
 }  // namespace lrn

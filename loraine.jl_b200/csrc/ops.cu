@@ -180,6 +180,103 @@ __global__ void k_scatter_ATy(int npos, const int* __restrict__ pos_p, const int
     for (int e = posptr[t]; e < posptr[t + 1]; e++) s += pos_val[e] * y[pos_row[e]];
     out[(size_t)pos_q[t] * ld + pos_p[t]] += scale * s;
 }
+// The three gather kernels below give one WARP to a position / row and let the lanes stride its list: lists are short on
+// average but skewed (a theta problem has one row with m entries), and a thread-per-row loop would serialise on it.
+__global__ void __launch_bounds__(256) k_pos_values(int npos, const int* __restrict__ posptr, const int* __restrict__ pos_row,
+                                                    const double* __restrict__ pos_val, const double* __restrict__ y,
+                                                    double* __restrict__ mval) {
+    const int t = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= npos) return;
+    double s = 0.0;
+    for (int e = posptr[t] + lane; e < posptr[t + 1]; e += 32) s += pos_val[e] * y[pos_row[e]];
+    s = warp_sum(s);
+    if (lane == 0) mval[t] = s;
+}
+// Z = M W (row r of the symmetric M is read as its column r).  Short rows: one thread per (r, q), gathering down column q
+// of W (L1/L2-resident).  The few long rows (a theta problem has one with m entries) get one warp per (r, q) in a second
+// launch, so no thread ever walks a long list alone.
+constexpr int MW_LONG = 32;
+__global__ void __launch_bounds__(256) k_M_times_W_short(int m, const int* __restrict__ pcolptr, const int* __restrict__ pos_p,
+                                                         const double* __restrict__ mval, const double* __restrict__ W, int ldw,
+                                                         double* __restrict__ Z, int ldz) {
+    const int r = blockIdx.x * 256 + threadIdx.x, q = blockIdx.y;
+    if (r >= m) return;
+    const int t0 = pcolptr[r], t1 = pcolptr[r + 1];
+    if (t1 - t0 > MW_LONG) return;
+    const double* Wq = W + (size_t)q * ldw;
+    double s = 0.0;
+    for (int t = t0; t < t1; t++) s += mval[t] * Wq[pos_p[t]];
+    Z[(size_t)q * ldz + r] = s;
+}
+__global__ void __launch_bounds__(256) k_M_times_W_long(int m, int nlong, const int* __restrict__ longrows,
+                                                        const int* __restrict__ pcolptr, const int* __restrict__ pos_p,
+                                                        const double* __restrict__ mval, const double* __restrict__ W, int ldw,
+                                                        double* __restrict__ Z, int ldz) {
+    const int q = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= m) return;
+    const int r = longrows[blockIdx.y];
+    const double* Wq = W + (size_t)q * ldw;
+    double s = 0.0;
+    for (int t = pcolptr[r] + lane; t < pcolptr[r + 1]; t += 32) s += mval[t] * Wq[pos_p[t]];
+    s = warp_sum(s);
+    if (lane == 0) Z[(size_t)q * ldz + r] = s;
+}
+// one warp per stored entry: eval[e] = v_e <W(:, p_e), Z(:, q_e)>.  Entry-parallel, so one dense constraint (e.g. the trace
+// constraint of a theta problem, m entries) does not serialise on a single warp; the per-constraint sums follow in k_row_sums
+__global__ void __launch_bounds__(256) k_A_sampled(long long nnz, int m, const int* __restrict__ ep, const int* __restrict__ eq,
+                                                   const double* __restrict__ ev, const double* __restrict__ W, int ldw,
+                                                   const double* __restrict__ Z, int ldz, double* __restrict__ eval) {
+    const long long e = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (e >= nnz) return;
+    const double* wp = W + (size_t)ep[e] * ldw;
+    const double* zq = Z + (size_t)eq[e] * ldz;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = lane;
+    for (; i + 96 < m; i += 128) {
+        a0 += wp[i] * zq[i];
+        a1 += wp[i + 32] * zq[i + 32];
+        a2 += wp[i + 64] * zq[i + 64];
+        a3 += wp[i + 96] * zq[i + 96];
+    }
+    for (; i < m; i += 32) a0 += wp[i] * zq[i];
+    const double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) eval[e] = ev[e] * s;
+}
+// one thread per stored entry: eval[e] = v_e sum_r ZY[p_e, r] U[q_e, r]
+__global__ void k_A_rank_entries(long long nnz, const int* __restrict__ ep, const int* __restrict__ eq,
+                                 const double* __restrict__ ev, const double* __restrict__ ZY, int ldz,
+                                 const double* __restrict__ U, int ldu, int k, double* __restrict__ eval) {
+    const long long e = (long long)blockIdx.x * TB + threadIdx.x;
+    if (e >= nnz) return;
+    double t = 0.0;
+    for (int r = 0; r < k; r++) t += ZY[(size_t)r * ldz + ep[e]] * U[(size_t)r * ldu + eq[e]];
+    eval[e] = ev[e] * t;
+}
+// one warp per constraint, fixed summation order: out[j] += scale * sum_{e in row j} eval[e]
+__global__ void __launch_bounds__(256) k_row_sums(int n_var, const int* __restrict__ rowptr, const double* __restrict__ eval,
+                                                  double scale, double* __restrict__ out) {
+    const int j = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= n_var) return;
+    const int e0 = rowptr[j], e1 = rowptr[j + 1];
+    if (e0 == e1) return;
+    double s = 0.0;
+    for (int e = e0 + lane; e < e1; e += 32) s += eval[e];
+    s = warp_sum(s);
+    if (lane == 0) out[j] += scale * s;
+}
+// Y(r, c) = sum_{t in column r of M} mval[t] X(pos_p[t], c)   (M symmetric: row r read as column r); one warp per (r, c)
+__global__ void __launch_bounds__(256) k_M_times_cols(int m, int k, const int* __restrict__ pcolptr, const int* __restrict__ pos_p,
+                                                      const double* __restrict__ mval, const double* __restrict__ X, int ldx,
+                                                      double* __restrict__ Y, int ldy) {
+    const int r = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31, c = blockIdx.y;
+    if (r >= m || c >= k) return;
+    const double* Xc = X + (size_t)c * ldx;
+    double s = 0.0;
+    for (int t = pcolptr[r] + lane; t < pcolptr[r + 1]; t += 32) s += mval[t] * Xc[pos_p[t]];
+    s = warp_sum(s);
+    if (lane == 0) Y[(size_t)c * ldy + r] = s;
+}
 __global__ void k_A_vec_thread(int n_var, const int* __restrict__ rowptr, const int* __restrict__ ep,
                                const int* __restrict__ eq, const double* __restrict__ ev, const double* __restrict__ M,
                                int ld, double scale, double* __restrict__ out) {
@@ -414,13 +511,52 @@ void sp_scatter_ATy(cudaStream_t st, const SparseBlock& sb, const double* y, dou
 }
 void sp_A_vec(cudaStream_t st, const SparseBlock& sb, const double* M, int ld, double scale, double* out) {
     if (sb.nnz == 0) return;
-    if (sb.nnz > 16LL * sb.n_var)
+    if (sb.nnz > 16LL * sb.n_var || sb.max_row_nnz > 64)      // long rows: lanes stride the row instead of one serial thread
         k_A_vec_warp<<<(unsigned)cdiv((long long)sb.n_var * 32, TB), TB, 0, st>>>(sb.n_var, sb.rowptr.p, sb.ep.p, sb.eq.p,
                                                                                   sb.ev.p, M, ld, scale, out);
     else
         k_A_vec_thread<<<(unsigned)cdiv(sb.n_var, TB), TB, 0, st>>>(sb.n_var, sb.rowptr.p, sb.ep.p, sb.eq.p, sb.ev.p, M, ld,
                                                                     scale, out);
     LRN_CHECK_LAUNCH();
+}
+void sp_pos_values(cudaStream_t st, SparseBlock& sb, const double* y) {
+    if (sb.npos == 0) return;
+    k_pos_values<<<(unsigned)cdiv((long long)sb.npos * 32, 256), 256, 0, st>>>(sb.npos, sb.posptr.p, sb.pos_row.p, sb.pos_val.p, y,
+                                                                              sb.mval.p);
+    LRN_CHECK_LAUNCH();
+}
+void sp_M_times_W(cudaStream_t st, const SparseBlock& sb, const double* W, int ldw, double* Z, int ldz) {
+    dim3 grid((unsigned)cdiv(sb.m, 256), (unsigned)sb.m);
+    k_M_times_W_short<<<grid, 256, 0, st>>>(sb.m, sb.pcolptr.p, sb.pos_p.p, sb.mval.p, W, ldw, Z, ldz);
+    LRN_CHECK_LAUNCH();
+    if (sb.nlong > 0) {
+        dim3 gl((unsigned)cdiv((long long)sb.m * 32, 256), (unsigned)sb.nlong);
+        k_M_times_W_long<<<gl, 256, 0, st>>>(sb.m, sb.nlong, sb.longrows.p, sb.pcolptr.p, sb.pos_p.p, sb.mval.p, W, ldw, Z, ldz);
+        LRN_CHECK_LAUNCH();
+    }
+}
+void sp_row_sums(cudaStream_t st, const SparseBlock& sb, double scale, double* out) {
+    k_row_sums<<<(unsigned)cdiv((long long)sb.n_var * 32, 256), 256, 0, st>>>(sb.n_var, sb.rowptr.p, sb.eval.p, scale, out);
+    LRN_CHECK_LAUNCH();
+}
+void sp_A_sampled(cudaStream_t st, SparseBlock& sb, const double* W, int ldw, const double* Z, int ldz, double scale,
+                  double* out) {
+    if (sb.nnz == 0) return;
+    k_A_sampled<<<(unsigned)cdiv(sb.nnz * 32, 256), 256, 0, st>>>(sb.nnz, sb.m, sb.ep.p, sb.eq.p, sb.ev.p, W, ldw, Z, ldz,
+                                                                  sb.eval.p);
+    LRN_CHECK_LAUNCH();
+    sp_row_sums(st, sb, scale, out);
+}
+void sp_M_times_cols(cudaStream_t st, const SparseBlock& sb, const double* X, int ldx, int k, double* Y, int ldy) {
+    dim3 grid((unsigned)cdiv((long long)sb.m * 32, 256), (unsigned)k);
+    k_M_times_cols<<<grid, 256, 0, st>>>(sb.m, k, sb.pcolptr.p, sb.pos_p.p, sb.mval.p, X, ldx, Y, ldy);
+    LRN_CHECK_LAUNCH();
+}
+void sp_A_rank(cudaStream_t st, SparseBlock& sb, const double* ZY, int ldz, const double* U, int ldu, int k, double* out) {
+    if (sb.nnz == 0) return;
+    k_A_rank_entries<<<(unsigned)cdiv(sb.nnz, TB), TB, 0, st>>>(sb.nnz, sb.ep.p, sb.eq.p, sb.ev.p, ZY, ldz, U, ldu, k, sb.eval.p);
+    LRN_CHECK_LAUNCH();
+    sp_row_sums(st, sb, 1.0, out);
 }
 void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int ldg, double* BG, int ldo) {
     dim3 grid((unsigned)cdiv(sb.n_var, TB), (unsigned)sb.m);

@@ -87,6 +87,15 @@ struct SparseBlock {
     int npos = 0;
     DevBuf<int> pos_p, pos_q, posptr, pos_row;
     DevBuf<double> pos_val;
+    // sparse-aware Schur operator (kit = 1): positions grouped by column (pcolptr, m + 1), values of mat(AA' y) per position;
+    // usable when every calA_j is stored symmetrically and the union pattern is sparse
+    DevBuf<int> pcolptr;
+    DevBuf<int> longrows;            // rows of the union pattern with more than 32 entries (handled warp-per-row)
+    int nlong = 0;
+    DevBuf<double> mval;
+    DevBuf<double> eval;             // one partial result per stored entry (entry-parallel kernels + deterministic row sums)
+    bool sparse_ok = false;          // structurally possible (symmetric storage, bounded rows)
+    bool sparse_op = false;          // in use (sparse_ok and union pattern density <= 5 %, or forced through lrn_set_option)
     // participating constraints (nnz > 0) in nnz-descending (sigmaA) order
     int npart = 0, nF1 = 0;
     DevBuf<int> part;
@@ -103,6 +112,20 @@ struct SparseBlock {
 void sp_scatter_ATy(cudaStream_t st, const SparseBlock& sb, const double* y, double scale, double* out, int ld);
 // out[j] += scale * sum_e ev * M[ep + eq*ld]                    (AA * vec(M), src/makeBBBB.jl:225 etc.)
 void sp_A_vec(cudaStream_t st, const SparseBlock& sb, const double* M, int ld, double scale, double* out);
+// Sparse-aware Schur operator pieces (MyA functor, src/Solvers.jl:572-614, without the two dense m^3 products):
+//   sp_pos_values : mval[t] = sum_{(j,v) at position t} v * y[j]                      (the nonzeros of M = mat(AA' y))
+//   sp_M_times_W  : Z = M W  (column q: gather from W(:,q) staged in shared memory, M row r = M column r by symmetry)
+//   sp_A_sampled  : out[j] += scale * sum_{(p,q,v) in calA_j} v * <W(:,p), Z(:,q)>     (= <calA_j, W M W>, W symmetric)
+void sp_pos_values(cudaStream_t st, SparseBlock& sb, const double* y);
+void sp_M_times_W(cudaStream_t st, const SparseBlock& sb, const double* W, int ldw, double* Z, int ldz);
+void sp_A_sampled(cudaStream_t st, SparseBlock& sb, const double* W, int ldw, const double* Z, int ldz, double scale,
+                  double* out);
+//   sp_M_times_cols : Y(:, c) = M X(:, c) for a thin X (m x k)                          (mat(AA' y) * U in the H_alpha apply)
+//   sp_A_rank       : out[j] += sum_{(p,q,v) in calA_j} v * sum_r ZY[p,r] U[q,r]        (AA * kron(U, Z y), src/Solvers.jl:891-896)
+//   sp_row_sums     : out[j] += scale * sum of sb.eval over the entries of row j        (second half of the entry-parallel kernels)
+void sp_M_times_cols(cudaStream_t st, const SparseBlock& sb, const double* X, int ldx, int k, double* Y, int ldy);
+void sp_A_rank(cudaStream_t st, SparseBlock& sb, const double* ZY, int ldz, const double* U, int ldu, int k, double* out);
+void sp_row_sums(cudaStream_t st, const SparseBlock& sb, double scale, double* out);
 // BG[j + c*ldo] = sum_t B[j,t] G[t,c]                           (B_i * G_i, src/makeBBBB.jl:7)
 void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int ldg, double* BG, int ldo);
 // Sparse-pair Schur term (F3 formula, src/makeBBBB.jl:139-213 / _dot :39-64): for participating positions jj <= kk, both >= first,

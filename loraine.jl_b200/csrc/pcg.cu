@@ -56,21 +56,73 @@ __global__ void k_build_AU(int n_var, const int* __restrict__ rowptr, const int*
     const double sc = rowscale ? rowscale[j] : 1.0;
     for (int e = rowptr[j]; e < rowptr[j + 1]; e++) AU[(size_t)ep[e] * ld + j] += sc * ev[e] * U[eq[e]];
 }
-// out[j] += sum_e v_e * sum_r ZY[p_e, r] * U[q_e, r]     (AA * kron(U, Z y), src/Solvers.jl:891-896)
-__global__ void k_A_vec_rank(int n_var, const int* __restrict__ rowptr, const int* __restrict__ ep, const int* __restrict__ eq,
-                             const double* __restrict__ ev, const double* __restrict__ ZY, int ldz,
-                             const double* __restrict__ U, int ldu, int k, double* __restrict__ out) {
-    int j = blockIdx.x * TBK + threadIdx.x;
-    if (j >= n_var) return;
-    int e0 = rowptr[j], e1 = rowptr[j + 1];
-    if (e0 == e1) return;
-    double s = 0.0;
-    for (int e = e0; e < e1; e++) {
-        double t = 0.0;
-        for (int r = 0; r < k; r++) t += ZY[(size_t)r * ldz + ep[e]] * U[(size_t)r * ldu + eq[e]];
-        s += ev[e] * t;
+// Thin products of the H_alpha apply (k = erank <= 8 columns): the DMMA tiles would be 1/64 full, these are plain
+// bandwidth-bound kernels instead.
+constexpr int THIN_K = 8;
+// out(i, c) = sum_r A(r, i) B(r, c): one warp per column i of A (coalesced along the column), shuffle reduction
+__global__ void __launch_bounds__(256) k_AtB_thin(const double* __restrict__ A, int lda, int rows, int cols,
+                                                  const double* __restrict__ B, int ldb, int k, double* __restrict__ out,
+                                                  int ldo) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= cols) return;
+    const double* a = A + (size_t)i * lda;
+    double acc[THIN_K];
+#pragma unroll
+    for (int c = 0; c < THIN_K; c++) acc[c] = 0.0;
+    for (int r = lane; r < rows; r += 32) {
+        const double av = a[r];
+#pragma unroll
+        for (int c = 0; c < THIN_K; c++)
+            if (c < k) acc[c] += av * B[(size_t)c * ldb + r];
     }
-    out[j] += s;
+#pragma unroll
+    for (int c = 0; c < THIN_K; c++) {
+        if (c >= k) break;
+        const double v = warp_sum(acc[c]);
+        if (lane == 0) out[(size_t)c * ldo + i] = v;
+    }
+}
+// out(r, c) = sum_i A(r, i) B(i, c): 32 rows x 8 column slices per CTA (coalesced 256 B row segments), shared-memory reduction
+__global__ void __launch_bounds__(256) k_AB_thin(const double* __restrict__ A, int lda, int rows, int cols,
+                                                 const double* __restrict__ B, int ldb, int k, double* __restrict__ out,
+                                                 int ldo) {
+    __shared__ double red[8][32];
+    const int rl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + rl;
+    const int chunk = (cols + 7) / 8, i0 = sl * chunk, i1 = min(cols, i0 + chunk);
+    for (int c = 0; c < k; c++) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (r < rows) {
+            const double* Bc = B + (size_t)c * ldb;
+            int i = i0;
+            for (; i + 3 < i1; i += 4) {
+                a0 += A[(size_t)i * lda + r] * Bc[i];
+                a1 += A[(size_t)(i + 1) * lda + r] * Bc[i + 1];
+                a2 += A[(size_t)(i + 2) * lda + r] * Bc[i + 2];
+                a3 += A[(size_t)(i + 3) * lda + r] * Bc[i + 3];
+            }
+            for (; i < i1; i++) a0 += A[(size_t)i * lda + r] * Bc[i];
+        }
+        red[sl][rl] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (sl == 0 && r < rows) {
+            double t = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) t += red[u][rl];
+            out[(size_t)c * ldo + r] = t;
+        }
+        __syncthreads();
+    }
+}
+void AtB_thin(cudaStream_t st, const double* A, int lda, int rows, int cols, const double* B, int ldb, int k, double* out, int ldo) {
+    if (k > THIN_K) { gemm_tn(st, cols, k, rows, 1.0, A, lda, B, ldb, 0.0, out, ldo); return; }
+    k_AtB_thin<<<(unsigned)cdiv((long long)cols * 32, 256), 256, 0, st>>>(A, lda, rows, cols, B, ldb, k, out, ldo);
+    LRN_CHECK_LAUNCH();
+}
+void AB_thin(cudaStream_t st, const double* A, int lda, int rows, int cols, const double* B, int ldb, int k, double* out, int ldo) {
+    if (k > THIN_K) { gemm_nn(st, rows, k, cols, 1.0, A, lda, B, ldb, 0.0, out, ldo); return; }
+    k_AB_thin<<<(unsigned)cdiv(rows, 32), 256, 0, st>>>(A, lda, rows, cols, B, ldb, k, out, ldo);
+    LRN_CHECK_LAUNCH();
 }
 
 struct PhaseT {   // minimal event timer (same bookkeeping as solver.cu)
@@ -243,10 +295,16 @@ void apply_alpha(lrn_solver* h, const double* x, double* out) {
     int off = 0;
     for (auto& B : h->blk) {
         const int m = B.m, ld = B.ld;
-        LRN_CUDA(cudaMemsetAsync(B.T1.p(), 0, B.T1.bytes(), st));
-        sp_scatter_ATy(st, B.sp, v, 1.0, B.T1.p(), ld);
-        gemm_nn(st, m, k, m, 1.0, B.T1.p(), ld, B.U.p(), B.U.ld, 0.0, B.MU.p(), B.MU.ld);
-        gemm_tn(st, m, k, m, 1.0, B.Zf.p(), ld, B.MU.p(), B.MU.ld, 0.0, h->pY.p + off, m);
+        if (B.sp.sparse_ok) {
+            // mat(AA' v) U without densifying: values per stored position, then a gather product with the thin U
+            sp_pos_values(st, B.sp, v);
+            sp_M_times_cols(st, B.sp, B.U.p(), B.U.ld, k, B.MU.p(), B.MU.ld);
+        } else {
+            LRN_CUDA(cudaMemsetAsync(B.T1.p(), 0, B.T1.bytes(), st));
+            sp_scatter_ATy(st, B.sp, v, 1.0, B.T1.p(), ld);
+            AB_thin(st, B.T1.p(), ld, m, m, B.U.p(), B.U.ld, k, B.MU.p(), B.MU.ld);
+        }
+        AtB_thin(st, B.Zf.p(), ld, m, m, B.MU.p(), B.MU.ld, k, h->pY.p + off, m);
         off += k * m;
     }
     chol_solve(h->pS.p, h->kS, pad_ld(h->kS), h->cholS, h->pY.p, h->pT.p /* scratch: t is only needed while S is being built */,
@@ -256,9 +314,8 @@ void apply_alpha(lrn_solver* h, const double* x, double* out) {
     off = 0;
     for (auto& B : h->blk) {
         const int m = B.m, ld = B.ld;
-        gemm_nn(st, m, k, m, 1.0, B.Zf.p(), ld, h->pY.p + off, m, 0.0, B.ZY.p(), B.ZY.ld);
-        k_A_vec_rank<<<nb(n), TBK, 0, st>>>(n, B.sp.rowptr.p, B.sp.ep.p, B.sp.eq.p, B.sp.ev.p, B.ZY.p(), B.ZY.ld, B.U.p(),
-                                            B.U.ld, k, yy2);
+        AB_thin(st, B.Zf.p(), ld, m, m, h->pY.p + off, m, k, B.ZY.p(), B.ZY.ld);
+        sp_A_rank(st, B.sp, B.ZY.p(), B.ZY.ld, B.U.p(), B.U.ld, k, yy2);
         off += k * m;
     }
     d_solve(h, yy2, out);
@@ -324,7 +381,11 @@ int32_t lrn_pcg(lrn_handle_t h, double tol, int64_t max_iter, int32_t kind, int6
         if (res0 <= tol) { *exit_code = 2; return LRN_OK; }
         apply_prec(h, kind, r, z);
         LRN_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        for (int64_t it = 1; it <= max_iter; it++) {
+        // One CG iteration is ~25 small launches (operator, preconditioner, vector updates) followed by ONE host read of the
+        // residual norm.  All operands live at fixed device addresses, so from the second iteration on the whole body
+        // -- z = M r, beta, p, Ap = A p, alpha, x, r, |r|^2 -- is replayed as a CUDA graph captured once per call (the first
+        // iteration runs eagerly and warms every lazily configured kernel / workspace).
+        auto part_a = [&]() {
             solver_apply_A(h, p, Ap);
             R.dot_vec(st, n, r, z, S_GAMMA, false);
             R.dot_vec(st, n, p, Ap, S_PAP, false);
@@ -332,15 +393,60 @@ int32_t lrn_pcg(lrn_handle_t h, double tol, int64_t max_iter, int32_t kind, int6
             k_cg_update<<<nb(n), TBK, 0, st>>>(n, R.slots.p, p, Ap, x, r);
             R.dot_vec(st, n, r, r, S_RR, false);
             LRN_CHECK_LAUNCH();
-            s = R.fetch(st);
-            if (s[S_FLAG] != 0.0 || std::isnan(s[S_ALPHA])) { *exit_code = -13; *num_iters = it; return LRN_OK; }
-            if (std::sqrt(s[S_RR]) / res0 <= tol) { *exit_code = 30; *num_iters = it; return LRN_OK; }
+        };
+        auto part_b = [&]() {
             apply_prec(h, kind, r, z);
             R.dot_vec(st, n, z, r, S_ZR, false);
             k_cg_beta<<<1, 1, 0, st>>>(R.slots.p);
             k_cg_p<<<nb(n), TBK, 0, st>>>(n, R.slots.p, z, p);
             LRN_CHECK_LAUNCH();
+        };
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        long long graph_nodes = 0;
+        bool use_graph = !gemm_profile_active() && max_iter >= 3;
+        auto release = [&]() {
+            if (gexec) cudaGraphExecDestroy(gexec);
+            if (graph) cudaGraphDestroy(graph);
+            gexec = nullptr; graph = nullptr;
+        };
+        for (int64_t it = 1; it <= max_iter; it++) {
+            if (it == 1) {
+                part_a();
+            } else if (it == 2 || !use_graph) {
+                part_b();          // eager once more: the preconditioner's second application still sees first-use set-up
+                part_a();
+            } else {
+                if (!gexec) {
+                    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                    if (ok) {
+                        const long long before = g_kernel_launches.load();
+                        try { part_b(); part_a(); } catch (...) { ok = false; }
+                        cudaGraph_t gcap = nullptr;
+                        if (cudaStreamEndCapture(st, &gcap) != cudaSuccess || !gcap) ok = false;
+                        graph = gcap;
+                        if (ok && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) ok = false;
+                        graph_nodes = g_kernel_launches.load() - before;
+                        g_kernel_launches.fetch_sub(graph_nodes);       // counted per replay below
+                    }
+                    if (!ok) {                                            // fall back to eager launches for the rest of the call
+                        cudaGetLastError();
+                        release();
+                        use_graph = false;
+                        part_b();
+                        part_a();
+                    }
+                }
+                if (gexec) {
+                    LRN_CUDA(cudaGraphLaunch(gexec, st));
+                    g_kernel_launches.fetch_add(graph_nodes);
+                }
+            }
+            s = R.fetch(st);
+            if (s[S_FLAG] != 0.0 || std::isnan(s[S_ALPHA])) { *exit_code = -13; *num_iters = it; release(); return LRN_OK; }
+            if (std::sqrt(s[S_RR]) / res0 <= tol) { *exit_code = 30; *num_iters = it; release(); return LRN_OK; }
         }
+        release();
         *exit_code = -2;
         *num_iters = max_iter;
         LRN_CUDA(cudaStreamSynchronize(st));

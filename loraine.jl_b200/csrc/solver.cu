@@ -173,6 +173,50 @@ void build_block(lrn_solver* h, Block& B) {
         pos_p.push_back(p); pos_q.push_back(q); posptr.push_back((int)w);
     }
     sp.npos = (int)pos_p.size();
+    {
+        // sparse-aware Schur operator (kit = 1): needs symmetric storage of every calA_j (entry (p,q,v) <=> (q,p,v)) and a
+        // sparse union pattern; otherwise the operator keeps the dense W M W form
+        std::vector<int> pcol(m + 1, 0);
+        for (size_t t = 0; t < pos_q.size(); t++) pcol[pos_q[t] + 1]++;
+        for (int q = 0; q < m; q++) pcol[q + 1] += pcol[q];
+        bool sym = true;
+        {
+            // positions are sorted by (q, p); (p,q) and (q,p) must carry identical (constraint, value) lists
+            auto find = [&](int p, int q) -> long long {
+                int lo = pcol[q], hi = pcol[q + 1];
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (pos_p[mid] < p) lo = mid + 1; else hi = mid; }
+                return (lo < pcol[q + 1] && pos_p[lo] == p) ? lo : -1;
+            };
+            for (size_t t = 0; t < pos_p.size() && sym; t++) {
+                if (pos_p[t] <= pos_q[t]) continue;
+                long long u = find(pos_q[t], pos_p[t]);
+                if (u < 0 || posptr[u + 1] - posptr[u] != posptr[t + 1] - posptr[t]) { sym = false; break; }
+                for (int a = posptr[t], b2 = posptr[u]; a < posptr[t + 1]; a++, b2++)
+                    if (pos_row[a] != pos_row[b2] || pos_val[a] != pos_val[b2]) { sym = false; break; }
+            }
+            // every strictly-upper position needs its mirror too: count check
+            long long lower = 0, upper = 0;
+            for (size_t t = 0; t < pos_p.size(); t++) { if (pos_p[t] > pos_q[t]) lower++; else if (pos_p[t] < pos_q[t]) upper++; }
+            if (lower != upper) sym = false;
+        }
+        int maxrow = 0;
+        for (int j = 0; j < n; j++) maxrow = std::max(maxrow, rowptr[j + 1] - rowptr[j]);
+        (void)maxrow;
+        sp.sparse_ok = sym && sp.npos > 0;
+        sp.sparse_op = sp.sparse_ok && (double)sp.npos <= 0.05 * (double)m * m;
+        if (sp.sparse_ok) {
+            sp.pcolptr.upload(pcol, h->st);
+            std::vector<int> longrows;
+            for (int r = 0; r < m; r++) if (pcol[r + 1] - pcol[r] > 32) longrows.push_back(r);
+            sp.nlong = (int)longrows.size();
+            if (sp.nlong > 0) sp.longrows.upload(longrows, h->st);
+            sp.mval.alloc((size_t)std::max(sp.npos, 1));
+        }
+        sp.eval.alloc((size_t)std::max<int64_t>(nnz, 1));
+        if (getenv("LRN_DEBUG_BUILD"))
+            fprintf(stderr, "[lrn build] block m=%d nnz=%lld npos=%d symmetric=%d sparse_ok=%d sparse_op=%d\n", m, (long long)nnz,
+                    sp.npos, (int)sym, (int)sp.sparse_ok, (int)sp.sparse_op);
+    }
     // participating constraints in nnz-descending stable order (= sigmaA restricted to nnz > 0, src/model.jl:157-160)
     std::vector<int> part;
     for (int j = 0; j < n; j++) if (rowptr[j + 1] > rowptr[j]) part.push_back(j);
@@ -286,6 +330,14 @@ void apply_A(lrn_solver* h, const double* x, double* out) {
     LRN_CUDA(cudaMemsetAsync(out, 0, (size_t)h->n_var * sizeof(double), st));
     for (auto& B : h->blk) {
         const int m = B.m, ld = B.ld;
+        if (B.sp.sparse_op) {
+            // M = mat(AA' x) is sparse: Z = M W by gathers, then <calA_j, W Z> sampled at the stored positions (HBM/L2-bound,
+            // 2 (npos + nnz) m flops instead of 4 m^3)
+            sp_pos_values(st, B.sp, x);
+            sp_M_times_W(st, B.sp, B.W.p(), ld, B.T2.p(), ld);
+            sp_A_sampled(st, B.sp, B.W.p(), ld, B.T2.p(), ld, 1.0, out);
+            continue;
+        }
         LRN_CUDA(cudaMemsetAsync(B.T1.p(), 0, B.T1.bytes(), st));
         sp_scatter_ATy(st, B.sp, x, 1.0, B.T1.p(), ld);
         gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
@@ -1086,6 +1138,14 @@ int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
         else if (n == "erank") { LRN_REQUIRE(h->prec_ready == 0, "erank cannot change after a preconditioner was built"); h->opt.erank = (int)value; }
         else if (n == "svd_tol") h->opt.svd_tol = value;
         else if (n == "lanczos_tol") h->opt.lanczos_tol = value;
+        else if (n == "sparse_op") {
+            // 0: dense W M W operator, 1: sparse-aware operator wherever the data allows it, -1: automatic (density rule)
+            for (auto& B : h->blk) {
+                if (value > 0) B.sp.sparse_op = B.sp.sparse_ok;
+                else if (value == 0) B.sp.sparse_op = false;
+                else B.sp.sparse_op = B.sp.sparse_ok && (double)B.sp.npos <= 0.05 * (double)B.m * B.m;
+            }
+        }
         else LRN_REQUIRE(false, "unknown option name");
         return LRN_OK;
     });

@@ -235,6 +235,34 @@ def test_cg_path_theta(pkg, golden_dir, prec):
     s.close()
 
 
+@pytest.mark.parametrize("gen,args", [("theta_torus", (6, 8)), ("multiblock_lp", (3, 12, 10, 7)), ("maxcut_torus", (6, 8, 3))])
+def test_cg_operator_sparse_and_dense_forms(pkg, gen, args):
+    """MyA (src/Solvers.jl:572-614): the sparse-aware operator (Z = M W by gathers, <calA_j, W Z> sampled) and the dense
+    W M W form give the oracle's result on the same iterate."""
+    from oracle import loraine_oracle as lo
+    from loraine_jl_b200 import solver as S
+    import ctypes as C
+    arrays = getattr(pkg.problems, gen)(*args)
+    o = dict(kit=1, preconditioner=0, initpoint=1, verb=0)
+    opt, ora = make_pair(pkg, arrays, o)
+    g, s = step_both(pkg, opt, ora, 2)
+    for mod, st in ((S, g), (lo, s)):
+        st.iter += 1; st.cg_iter_pre = st.cg_iter_cor = 0
+        mod.find_mu(st); mod.prepare_W(st)
+    x = np.random.default_rng(7).standard_normal(s.model.n)
+    ref = lo.MyA(s)(x)
+    dpx = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    outs = []
+    for mode in (1.0, 0.0):
+        g._call("lrn_set_option", b"sparse_op", mode)
+        out = np.zeros_like(x)
+        g._call("lrn_apply_operator", -1, dpx(x), dpx(out))
+        assert relerr(out, ref) <= 1e-8
+        outs.append(out)
+    assert relerr(outs[0], outs[1]) <= 1e-11
+    g.close()
+
+
 def test_cg_operator_and_preconditioner_apply(pkg):
     """MyA and MyM applied to a random vector vs the oracle's functors on the same iterate (LP block included)."""
     from oracle import loraine_oracle as lo
