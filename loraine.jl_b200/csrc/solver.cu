@@ -792,9 +792,16 @@ int32_t lrn_rhs_predictor(lrn_handle_t h) {
             const int m = B.m, ld = B.ld;
             // h += AA * vec(W (Rd + S) W)                                     (src/makeBBBB.jl:225)
             mat_lincomb(st, m, m, B.T1.p(), ld, 1.0, B.Rd.p(), ld, 1.0, B.S.p(), ld, 0.0, nullptr, 0);
-            gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
-            gemm_sym(st, false, false, m, B.T2.p(), ld, B.W.p(), ld, B.T3.p(), ld);
-            sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
+            if ((double)B.sp.nnz <= 0.05 * (double)m * m) {
+                // sparse data: <calA_j, W T W> is only needed at the stored positions -- Z = T W (one product), then one
+                // m-long inner product <W(:,p), Z(:,q)> per stored entry instead of the second m^3 product
+                gemm_nn(st, m, m, m, 1.0, B.T1.p(), ld, B.W.p(), ld, 0.0, B.T2.p(), ld);
+                sp_A_sampled(st, B.sp, B.W.p(), ld, B.T2.p(), ld, 1.0, h->rhs.p);
+            } else {
+                gemm_nn(st, m, m, m, 1.0, B.W.p(), ld, B.T1.p(), ld, 0.0, B.T2.p(), ld);
+                gemm_sym(st, false, false, m, B.T2.p(), ld, B.W.p(), ld, B.T3.p(), ld);
+                sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
+            }
         }
         add_lp_rhs(h, 0, 0.0);
         return LRN_OK;
@@ -814,9 +821,17 @@ int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
             gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
             gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
             mat_corr_inner(st, m, B.T2.p(), ld, B.D.p, sm, B.RNT.p(), ld);
-            gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.T2.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_sym(st, false, true, m, B.T1.p(), ld, B.G.p(), ld, B.T3.p(), ld);
-            sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
+            if ((double)B.sp.nnz <= 0.05 * (double)m * m) {
+                // sparse data: (G K G')(p,q) = <(K G')(:,p), G'(:,q)> (K symmetric) is only needed at the stored positions:
+                // one product K G', an explicit G' (T4 is free here) and one m-long inner product per stored entry
+                gemm_nt(st, m, m, m, 1.0, B.T2.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+                mat_transpose(st, m, B.T4.p(), ld, B.G.p(), ld);
+                sp_A_sampled(st, B.sp, B.T1.p(), ld, B.T4.p(), ld, 1.0, h->rhs.p);
+            } else {
+                gemm_nn(st, m, m, m, 1.0, B.G.p(), ld, B.T2.p(), ld, 0.0, B.T1.p(), ld);
+                gemm_sym(st, false, true, m, B.T1.p(), ld, B.G.p(), ld, B.T3.p(), ld);
+                sp_A_vec(st, B.sp, B.T3.p(), ld, 1.0, h->rhs.p);
+            }
         }
         add_lp_rhs(h, 1, sm);
         return LRN_OK;
