@@ -574,6 +574,7 @@ int32_t lrn_set_iterate(lrn_handle_t h, const double* const* X, const double* co
             upload_dense(h, h->blk[i].X, X[i]);
             upload_dense(h, h->blk[i].S, S[i]);
             h->blk[i].chol_cached = false;
+            h->blk[i].rdb_valid = false;
         }
         LRN_REQUIRE(y, "null y");
         h->y.upload(y, h->n_var, h->st);
@@ -624,6 +625,18 @@ static void gemm_sym(cudaStream_t st, bool ta, bool tb, int m, const double* A, 
     mat_mirror_lower(st, m, C, ldc);
 }
 
+// Sparse data: delS = Rd - M with a sparse M = mat(AA' dely), so G' delS G = G' Rd G - G' (M G).  G' Rd G is formed once per
+// iteration (Rd and G are fixed between lrn_residuals / lrn_prepare_W calls); M G is a gather product.
+static bool use_rdb(const Block& B) { return B.sp.sparse_ok && (double)B.sp.npos <= 0.05 * (double)B.m * B.m; }
+static void ensure_rdb(lrn_solver* h, Block& B) {
+    if (B.rdb_valid) return;
+    const int m = B.m, ld = B.ld;
+    if (!B.RdB.p()) B.RdB.init(m, m);
+    gemm_nn(h->st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+    gemm_sym(h->st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.RdB.p(), B.RdB.ld);
+    B.rdb_valid = true;
+}
+
 // ---- hot path -------------------------------------------------------------------------------------------------------
 int32_t lrn_find_mu(lrn_handle_t h, double* mu) {
     return guarded(h, [&]() -> int32_t {
@@ -652,6 +665,7 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
                 if ((!okx || !oks) && status4) *status4 = 1;
             }
             B.chol_cached = false;
+            B.rdb_valid = false;
             zero_strict_upper(B.LX.p(), m, ld, st);
             zero_strict_upper(B.LS.p(), m, ld, st);
             // CC = L_S' L_X                                                   (src/prepare_W.jl:39)
@@ -705,6 +719,7 @@ int32_t lrn_residuals(lrn_handle_t h) {
         const int n = h->n_var;
         LRN_CUDA(cudaMemcpyAsync(h->Rp.p, h->b.p, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
         for (auto& B : h->blk) {
+            B.rdb_valid = false;
             sp_A_vec(st, B.sp, B.X.p(), B.ld, -1.0, h->Rp.p);
             mat_lincomb(st, B.m, B.m, B.Rd.p(), B.ld, 1.0, B.C.p(), B.C.ld, -1.0, B.S.p(), B.ld, 0.0, nullptr, 0);
             sp_scatter_ATy(st, B.sp, h->y.p, -1.0, B.Rd.p(), B.ld);
@@ -818,8 +833,13 @@ int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
         for (auto& B : h->blk) {
             const int m = B.m, ld = B.ld;
             // h += AA * vec(G (G' Rd G + diag(D) - diag(sigma mu ./ D) - RNT) G')      (src/predictor_corrector.jl:186)
-            gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
+            if (use_rdb(B)) {
+                ensure_rdb(h, B);
+                LRN_CUDA(cudaMemcpyAsync(B.T2.p(), B.RdB.p(), B.RdB.bytes(), cudaMemcpyDeviceToDevice, st));
+            } else {
+                gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+                gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
+            }
             mat_corr_inner(st, m, B.T2.p(), ld, B.D.p, sm, B.RNT.p(), ld);
             if ((double)B.sp.nnz <= 0.05 * (double)m * m) {
                 // sparse data: (G K G')(p,q) = <(K G')(:,p), G'(:,q)> (K symmetric) is only needed at the stored positions:
@@ -896,8 +916,20 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
             LRN_CUDA(cudaMemcpyAsync(B.dS.p(), B.Rd.p(), B.Rd.bytes(), cudaMemcpyDeviceToDevice, st));
             sp_scatter_ATy(st, B.sp, h->dely.p, -1.0, B.dS.p(), ld);
             // delSb = G' delS G                                                (:263)
-            gemm_nn(st, m, m, m, 1.0, B.dS.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
-            gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
+            if (use_rdb(B)) {
+                ensure_rdb(h, B);
+                sp_pos_values(st, B.sp, h->dely.p);
+                sp_M_times_W(st, B.sp, B.G.p(), ld, B.T1.p(), ld);                      // T1 = M G
+                LRN_CUDA(cudaMemcpyAsync(B.T2.p(), B.RdB.p(), B.RdB.bytes(), cudaMemcpyDeviceToDevice, st));
+                GemmParams p;                                                            // T2 = G'RdG - G'(M G), lower + mirror
+                p.A = B.G.p(); p.B = B.T1.p(); p.C = B.T2.p(); p.M = m; p.N = m; p.K = m; p.lda = ld; p.ldb = ld; p.ldc = ld;
+                p.transA = true; p.alpha = -1.0; p.beta = 1.0; p.lower = 1;
+                gemm(p, st);
+                mat_mirror_lower(st, m, B.T2.p(), ld);
+            } else {
+                gemm_nn(st, m, m, m, 1.0, B.dS.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+                gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.T2.p(), ld);
+            }
             // delX = mat(-X - W delS W)                         (predictor, :255)
             //      = mat(sigma mu Si - X - W delS W + G RNT G') (corrector, :257)
             // with W = G G' both congruences collapse into ONE:  delX = mat([sigma mu Si] - X + G (RNT - delSb) G')

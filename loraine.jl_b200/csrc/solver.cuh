@@ -27,6 +27,8 @@ struct Block {
     DMat C;
     double normC = 0.0;
     DMat X, S, dX, dS, Xn, Sn, G, Gi, W, Si, Rd, RNT, LX, LS, T1, T2, T3, T4;
+    DMat RdB;                          // G' Rd G of the current iteration (sparse data: shared by both find_steps and the corrector RHS)
+    bool rdb_valid = false;
     DevBuf<double> D, DDsi, dm12, dm32, vtmp;
     CholWork cholX, cholS;
     SvdWork svd;
