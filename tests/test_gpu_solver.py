@@ -104,6 +104,33 @@ def test_first_iterations_match_oracle(pkg, golden_dir, name, nblk):
     g.close()
 
 
+@pytest.mark.parametrize("datarank", [-1, 0])
+def test_sparse_data_forms_match_oracle(pkg, datarank):
+    """m = 192 max-cut instance: the stored positions are < 5 % of m^2, so the RHS congruences are sampled at the stored
+    positions, G'RdG is shared across the iteration and G'(MG) is a gather product (lrn_rhs_*, lrn_find_step); the iterates
+    must follow the oracle, which evaluates the reference's dense formulas (src/predictor_corrector.jl:183-192, :248-326)."""
+    from loraine_jl_b200 import solver as S
+    arrays = pkg.problems.maxcut_torus(12, 16, 11)
+    opt, ora = make_pair(pkg, arrays, dict(kit=0, datarank=datarank, initpoint=1, verb=0))
+    g, s = step_both(pkg, opt, ora, 3)
+    lo = ora[0]
+    y, X, _ = S.get_solution(g)
+    assert relerr(y, s.y) <= 1e-7
+    assert relerr(X[0], s.X[0]) <= 1e-7
+    for side, mod, st, ha in ((0, S, g, opt.halpha), (1, lo, s, ora[2])):
+        st.iter += 1
+        mod.find_mu(st)
+        mod.prepare_W(st)
+        mod.predictor(st, ha)
+    assert relerr(g.get_array("DELY"), s.dely) <= 1e-7
+    assert np.allclose(g.alpha, s.alpha, rtol=1e-6) and np.allclose(g.beta, s.beta, rtol=1e-6)
+    assert abs(S.sigma_update(g) - lo.sigma_update(s)) <= 1e-6
+    S.corrector(g, opt.halpha)
+    lo.corrector(s, ora[2])
+    assert relerr(g.get_array("DELY"), s.dely) <= 1e-6
+    g.close()
+
+
 def test_schur_matrix_parity_1e11(pkg, golden_dir):
     """north_star: assembled Schur matrix within 1e-11 relative Frobenius error for the SAME W (general + LP + rank-one)."""
     from oracle import loraine_oracle as lo
