@@ -450,3 +450,100 @@ def test_large_blocks_properties_C2_quarter(pkg):
     assert relerr(H, W ** 2) <= 1e-11                          # b_k = e_k  =>  H = (W).^2
     assert g._call("lrn_schur_factor") == 0
     g.close()
+
+
+def test_full_size_C2_properties(pkg):
+    """BASELINE configs[1] at full size (max-cut n = m = 5000, datarank = -1): size-independent properties of one iteration,
+    the heavy products checked against cuBLAS FP64 through torch (an implementation independent of this library):
+    W S W = X, G' S G = D, H = W.^2 (F_k = e_k e_k'), L L' = H, H dely = rhs, and the predictor step keeps X, S positive
+    definite (alpha, beta in (0, 1])."""
+    import ctypes as C
+    import torch
+    from loraine_jl_b200 import solver as S
+    cfg = pkg.problems.CONFIGS["C2"]
+    opt = pkg.Optimizer()
+    for k, v in dict(cfg["options"], verb=0).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*cfg["gen"]()))
+    g = opt.solver
+    S.setup_solver(g, opt.halpha); S.initial_point(g)
+    for _ in range(2):
+        S.myIPstep(g, opt.halpha); g.itertime = 0.0; S.check_convergence(g)
+    g.iter += 1
+    S.find_mu(g); S.prepare_W(g)
+    m = g.model.msizes[0]
+    assert m == 5000 and g.model.n == 5000
+    dev = torch.device("cuda")
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rel = lambda a, b: float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+    W, G, D = T(g.get_array("W", 0)), T(g.get_array("G", 0)), T(g.get_array("D", 0))
+    y, X, _ = S.get_solution(g)
+    Sm = [np.zeros((m, m), order="F")]
+    Sp = (C.POINTER(C.c_double) * 1)(Sm[0].ctypes.data_as(C.POINTER(C.c_double)))
+    g._call("lrn_get_slack", Sp, None)
+    Xt, St = T(X[0]), T(Sm[0])
+    assert rel(W @ St @ W, Xt) <= 1e-10
+    assert rel(G.T @ St @ G, torch.diag(D)) <= 1e-10
+    S.predictor(g, opt.halpha)                                  # residuals, assembly, RHS, factorisation, solve, find_step
+    H = T(g.get_array("H"))
+    Hl = torch.tril(H)
+    Hs = Hl + torch.tril(H, -1).T                               # the library fills (at least) the lower triangle
+    assert rel(Hs, W * W) <= 1e-11                              # b_k = e_k  =>  H = W.^2
+    L = torch.tril(T(g.get_array("L")))
+    assert rel(L @ L.T, Hs) <= 1e-12
+    dely, rhs = T(g.get_array("DELY")), T(g.get_array("RHS"))
+    assert rel(Hs @ dely, rhs) <= 1e-9
+    assert 0.0 < g.alpha[0] <= 1.0 and 0.0 < g.beta[0] <= 1.0
+    g.close()
+
+
+def schur_entry_ref(AA_csr, W, j, k):
+    """H[j,k] = tr(A_j W A_k W) = sum_{(p,q) in A_j} sum_{(r,c) in A_k} a_pq a_rc W[q,r] W[c,p]  (src/makeBBBB.jl:39-64),
+    A_j = mat(row j of AA) with vec index p + q*m."""
+    m = W.shape[0]
+    rj, rk = AA_csr.getrow(int(j)), AA_csr.getrow(int(k))
+    pj, qj, vj = rj.indices % m, rj.indices // m, rj.data
+    pk, qk, vk = rk.indices % m, rk.indices // m, rk.data
+    # sum_{e in j} sum_{f in k} vj_e vk_f W[qj_e, pk_f] W[qk_f, pj_e]
+    return float(np.einsum("e,f,ef,ef->", vj, vk, W[np.ix_(qj, pk)], W[np.ix_(pj, qk)]))
+
+
+def test_full_size_C5_properties(pkg):
+    """BASELINE configs[4] at full size (n_var = 40 000, one block m = 1000, general sparse assembly + 12.8 GB Cholesky):
+    sampled entries of H against the defining formula tr(A_j W A_k W) evaluated in NumPy from the downloaded W,
+    L L' = H against cuBLAS FP64 (torch), and H dely = rhs."""
+    import torch
+    from loraine_jl_b200 import solver as S
+    cfg = pkg.problems.CONFIGS["C5"]
+    opt = pkg.Optimizer()
+    for k, v in dict(cfg["options"], verb=0).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*cfg["gen"]()))
+    g = opt.solver
+    S.setup_solver(g, opt.halpha); S.initial_point(g)
+    S.myIPstep(g, opt.halpha); g.itertime = 0.0; S.check_convergence(g)
+    g.iter += 1
+    S.find_mu(g); S.prepare_W(g)
+    S.predictor(g, opt.halpha)
+    md = g.model
+    n, m = md.n, md.msizes[0]
+    assert n == 40000 and m == 1000
+    W = g.get_array("W", 0)
+    H = g.get_array("H")
+    AA = md.AA[0].tocsr()
+    rng = np.random.default_rng(0)
+    js, ks = rng.integers(0, n, 200), rng.integers(0, n, 200)
+    ref = np.array([schur_entry_ref(AA, W, j, k) for j, k in zip(js, ks)])
+    got = H[js, ks]
+    assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    dev = torch.device("cuda")
+    Ht = torch.from_numpy(H).to(dev)
+    Lt = torch.tril(torch.from_numpy(g.get_array("L")).to(dev))
+    R = Lt @ Lt.T
+    R -= Ht
+    assert float(torch.linalg.norm(R) / torch.linalg.norm(Ht)) <= 1e-12
+    del R, Lt
+    dely = torch.from_numpy(g.get_array("DELY")).to(dev)
+    rhs = torch.from_numpy(g.get_array("RHS")).to(dev)
+    assert float(torch.linalg.norm(Ht @ dely - rhs) / torch.linalg.norm(rhs)) <= 1e-9
+    g.close()
