@@ -318,6 +318,9 @@ def run_b200(args):
         clocks=clocks,
         solve=solve_info,
         phases_ms_per_iteration={k: v[0] / args.steps for k, v in phase.items()},
+        # CUDA-event time of the ABI calls of one step on the library stream (nested phases svd / eigmin not double counted);
+        # `value` is the host clock around the same steps between device synchronisations and also contains the host logic
+        device_event_ms_per_step=sum(v[0] for k, v in phase.items() if k not in ("svd", "eigmin")) / args.steps,
         schur=dict(assemble_ms=asm_ms, assemble_tflops=alg["assemble"] / (asm_ms * 1e-3) / 1e12 if asm_ms > 0 else None,
                    factor_ms=fac_ms, factor_tflops=alg["factor"] / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else None,
                    assemble_plus_factor_tflops=(alg["assemble"] + alg["factor"]) / ((asm_ms + fac_ms) * 1e-3) / 1e12
