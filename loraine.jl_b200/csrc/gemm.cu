@@ -197,14 +197,17 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// TMA-fed variant for the two named FP64 hot kernels (Schur SYRK with squared epilogue, Cholesky trailing update): both are
-// C (+)= f(A B^T) with MN-major operands, so one k-line of a 128-wide tile is a contiguous 1 KB segment in global memory.
+// TMA-fed variant for the large products (Schur SYRK with squared epilogue, Cholesky trailing update, the m x m congruences):
+// with an MN-major operand one k-line of a 128-wide tile is a contiguous 1 KB segment in global memory (a K-major B operand
+// is moved as 128 segments of 256 B).
 // A dedicated producer warp moves those segments with the bulk-copy engine (cp.async.bulk -> SASS UBLKCP) into the padded
 // shared-memory rows and signals mbarriers; the 8 consumer warps never touch a load instruction or a block barrier in the
 // main loop.  Full 128 x 128 tiles only (the host sends edge strips to the cp.async kernel), K % 32 == 0.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int BKB = 32, STB = 3, LDT = 128 + 4;
-constexpr int BULK_STAGE_ELEMS = 2 * BKB * LDT;
+constexpr int BKB = 32, STB = 3, LDT = 128 + 4, LDK = BKB + 4;
+constexpr int BULK_A_ELEMS = BKB * LDT;                      // A tile: [k][128 + 4]
+constexpr int BULK_B_ELEMS = 128 * LDK;                      // B tile: [k][128 + 4] (A B^T) or [n][32 + 4] (A B); the larger one
+constexpr int BULK_STAGE_ELEMS = BULK_A_ELEMS + BULK_B_ELEMS;
 constexpr size_t BULK_SMEM = (size_t)STB * BULK_STAGE_ELEMS * sizeof(double) + 64;
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -232,7 +235,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(288) dgemm_dmma_bulk_nt_kernel(const GemmParams p) {
+// TB = true : C (+)= f(A B^T), B is N x K stored N-major (k-lines of 1 KB, like A)
+// TB = false: C (+)= A B,       B is K x N column-major: one 256 B segment (32 k) per column of the tile, stored [n][32 + 4]
+template <bool TB>
+__global__ void __launch_bounds__(288, 1) dgemm_dmma_bulk_kernel(const GemmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
     if (p.lower && (m0 + 127 < n0)) return;
@@ -248,17 +254,27 @@ __global__ void __launch_bounds__(288) dgemm_dmma_bulk_nt_kernel(const GemmParam
     if (warp == 8) {
         // ---- producer warp: lane l moves k-line l of the A tile and of the B tile -----------------------------------
         const double* Ag = p.A + m0;
-        const double* Bg = p.B + n0;
+        const double* Bg = TB ? p.B + n0 : p.B + (size_t)n0 * p.ldb;
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % STB;
             mbar_wait(bars + 8 * (STB + s), ((kt / STB) & 1) ^ 1);
             if (lane == 0) mbar_expect_tx(bars + 8 * s, 2u * BKB * 128u * 8u);
             __syncwarp();
-            const uint32_t sa = sbase + (uint32_t)((s * BULK_STAGE_ELEMS + lane * LDT) * sizeof(double));
-            const uint32_t sb = sa + (uint32_t)(BKB * LDT * sizeof(double));
+            const uint32_t st0 = sbase + (uint32_t)(s * BULK_STAGE_ELEMS * sizeof(double));
+            const uint32_t sa = st0 + (uint32_t)(lane * LDT * sizeof(double));
             const size_t k = (size_t)kt * BKB + lane;
             bulk_g2s(sa, Ag + k * p.lda, 128u * 8u, bars + 8 * s);
-            bulk_g2s(sb, Bg + k * p.ldb, 128u * 8u, bars + 8 * s);
+            if (TB) {
+                const uint32_t sb = st0 + (uint32_t)((BULK_A_ELEMS + lane * LDT) * sizeof(double));
+                bulk_g2s(sb, Bg + k * p.ldb, 128u * 8u, bars + 8 * s);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int n = lane + 32 * q;
+                    const uint32_t sb = st0 + (uint32_t)((BULK_A_ELEMS + n * LDK) * sizeof(double));
+                    bulk_g2s(sb, Bg + (size_t)n * p.ldb + (size_t)kt * BKB, BKB * 8u, bars + 8 * s);
+                }
+            }
         }
         return;
     }
@@ -274,14 +290,14 @@ __global__ void __launch_bounds__(288) dgemm_dmma_bulk_nt_kernel(const GemmParam
         const int s = kt % STB;
         mbar_wait(bars + 8 * s, (kt / STB) & 1);
         const double* sA = smem + (size_t)s * BULK_STAGE_ELEMS;
-        const double* sB = sA + BKB * LDT;
+        const double* sB = sA + BULK_A_ELEMS;
 #pragma unroll
         for (int kk = 0; kk < BKB; kk += 4) {
             double a[8], b[4];
 #pragma unroll
             for (int i = 0; i < 8; i++) a[i] = sA[(kk + lk) * LDT + wm0 + i * 8 + lr];
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = sB[(kk + lk) * LDT + wn0 + j * 8 + lr];
+            for (int j = 0; j < 4; j++) b[j] = TB ? sB[(kk + lk) * LDT + wn0 + j * 8 + lr] : sB[(wn0 + j * 8 + lr) * LDK + kk + lk];
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -475,10 +491,11 @@ void launch_trans(const GemmParams& p, cudaStream_t st) {
 
 namespace {
 bool g_bulk_enabled = true;
-void launch_bulk_nt(const GemmParams& p, cudaStream_t st) {
+void launch_bulk(const GemmParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(dgemm_dmma_bulk_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BULK_SMEM));
+        LRN_CUDA(cudaFuncSetAttribute(dgemm_dmma_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BULK_SMEM));
+        LRN_CUDA(cudaFuncSetAttribute(dgemm_dmma_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BULK_SMEM));
         configured = true;
     }
     dim3 grid((unsigned)(p.M / 128), (unsigned)(p.N / 128));
@@ -490,7 +507,8 @@ void launch_bulk_nt(const GemmParams& p, cudaStream_t st) {
         rec.flops = 2.0 * p.M * (double)p.N * p.K * (p.lower ? 0.5 : 1.0);
         LRN_CUDA(cudaEventRecord(rec.a, st));
     }
-    dgemm_dmma_bulk_nt_kernel<<<grid, 288, BULK_SMEM, st>>>(p);
+    if (p.transB) dgemm_dmma_bulk_kernel<true><<<grid, 288, BULK_SMEM, st>>>(p);
+    else dgemm_dmma_bulk_kernel<false><<<grid, 288, BULK_SMEM, st>>>(p);
     LRN_CHECK_LAUNCH();
     if (prof) {
         LRN_CUDA(cudaEventRecord(rec.b, st));
@@ -534,15 +552,25 @@ void gemm_set_bulk(bool on) { g_bulk_enabled = on; }
 
 void gemm(const GemmParams& p, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
-    // TMA (bulk copy) path: large A B^T products with 16-byte aligned MN-major operands and K % 32 == 0
-    if (g_bulk_enabled && !p.ktri && !p.transA && p.transB && p.batch == 1 && p.batch2 == 1 && !p.colscale && !p.cblkmap && p.K >= 64 &&
-        p.K % 32 == 0 && p.M >= 1024 && p.N >= 1024 && p.row0 == 0 && p.col0 == 0 &&
+    // TMA (bulk copy) path: large A B^T and A B products with 16-byte aligned operands.  The kernel takes whole 128 x 128
+    // tiles and K in multiples of 32; the bottom / right edge strips and a K remainder (added with beta = 1, plain epilogue
+    // only) go through the generic kernel.
+    const int Kf = p.K / 32 * 32;
+    if (g_bulk_enabled && !p.ktri && !p.transA && p.batch == 1 && p.batch2 == 1 && !p.colscale && !p.cblkmap && Kf >= 64 &&
+        (Kf == p.K || p.mode == 0) && p.M >= 1024 && p.N >= 1024 && p.row0 == 0 && p.col0 == 0 &&
         ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && p.lda % 2 == 0 && p.ldb % 2 == 0) {
         const int Mf = p.M / 128 * 128, Nf = p.N / 128 * 128;
         GemmParams f = p;
-        f.M = Mf; f.N = Nf;
-        launch_bulk_nt(f, stream);
-        g_bulk_enabled = false;                  // the edge strips go through the generic path below
+        f.M = Mf; f.N = Nf; f.K = Kf;
+        launch_bulk(f, stream);
+        g_bulk_enabled = false;                  // the remainders go through the generic path below
+        if (Kf < p.K) {                          // K remainder on the full-tile region
+            GemmParams e = f;
+            e.A = p.A + (size_t)Kf * p.lda;
+            e.B = p.transB ? p.B + (size_t)Kf * p.ldb : p.B + Kf;
+            e.K = p.K - Kf; e.beta = 1.0;
+            gemm(e, stream);
+        }
         if (Mf < p.M) {                          // bottom strip: rows [Mf, M), all columns
             GemmParams e = p;
             e.A = p.A + Mf; e.C = p.C + Mf; e.M = p.M - Mf; e.row0 = Mf;
@@ -550,7 +578,8 @@ void gemm(const GemmParams& p, cudaStream_t stream) {
         }
         if (Nf < p.N) {                          // right strip: rows [0, Mf), columns [Nf, N)
             GemmParams e = p;
-            e.B = p.B + Nf; e.C = p.C + (size_t)Nf * p.ldc; e.M = Mf; e.N = p.N - Nf; e.col0 = Nf;
+            e.B = p.transB ? p.B + Nf : p.B + (size_t)Nf * p.ldb;
+            e.C = p.C + (size_t)Nf * p.ldc; e.M = Mf; e.N = p.N - Nf; e.col0 = Nf;
             gemm(e, stream);
         }
         g_bulk_enabled = true;

@@ -76,6 +76,26 @@ def test_gemm_tma_bulk_path(L, M, N, K, lower, mode):
         assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want)
 
 
+@pytest.mark.parametrize("M,N,K,tb,lower,beta", [(1024, 1024, 64, 0, 0, 0.0), (1100, 1300, 104, 0, 0, 1.0), (1300, 1100, 1000, 0, 0, 0.5),
+                                                 (1500, 1500, 1500, 0, 1, 0.0), (1500, 1500, 1500, 1, 1, 0.0), (1030, 2000, 77, 1, 0, 1.0)])
+def test_gemm_tma_bulk_nn_and_k_remainder(L, M, N, K, tb, lower, beta):
+    """A B products (K-major B operand moved as 256 B segments) and K % 32 != 0 (remainder added by the generic kernel)."""
+    rng = np.random.default_rng(M + 3 * N + 7 * K + tb)
+    A = rng.standard_normal((M, K))
+    B = rng.standard_normal((N, K)) if tb else rng.standard_normal((K, N))
+    if lower:                                     # symmetric product: B = A' (or A for the transposed form)
+        B = A[:N] if tb else A[:N].T.copy()
+    C0 = rng.standard_normal((M, N))
+    P = A @ (B.T if tb else B)
+    want = beta * C0 + 1.25 * P
+    got = run_gemm(L, A, B, C0, 0, tb, 1.25, beta, mode=0, lower=lower)
+    if lower:
+        il = np.tril_indices(min(M, N))
+        assert np.linalg.norm(got[il] - want[il]) <= 1e-13 * np.linalg.norm(want[il])
+    else:
+        assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want)
+
+
 def test_gemm_unaligned_colscale_beta0_nan_safe(L):
     rng = np.random.default_rng(5)
     A, B = rng.standard_normal((123, 77)), rng.standard_normal((77, 95))
