@@ -305,6 +305,18 @@ def run_b200(args):
     asm_ms = phase["schur_assemble"][0] / max(1, phase["schur_assemble"][1])
     fac_ms = phase["schur_factor"][0] / max(1, phase["schur_factor"][1])
     achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+    # per-kernel split of the same profile: the roofline object describes the kernel with the largest share of the step
+    fams = []
+    for code, kname in ((10, "dgemm_dmma_kernel (cp.async-fed DMMA GEMM: congruences, Gram products, TRSM, edge strips)"),
+                        (11, "dgemm_dmma_bulk_kernel (TMA-fed DMMA GEMM: Schur SYRK, Cholesky trailing updates, large congruences)"),
+                        (12, "panel_rotate_kernel (TMA-fed DMMA panel rotation of the block-Jacobi SVD)")):
+        fm, ff, fn = C.c_double(), C.c_double(), C.c_int64()
+        L.lrn_dbg_gemm_profile(code, C.byref(fm), C.byref(ff), C.byref(fn))
+        if fn.value > 0 and fm.value > 0:
+            fams.append(dict(kernel=kname, launches=int(fn.value), kernel_ms_per_step=fm.value / prof_steps,
+                             algorithmic_flops_per_launch=ff.value / fn.value,
+                             avg_launch_us=1e3 * fm.value / fn.value, achieved=ff.value / (fm.value * 1e-3) / 1e12))
+    dom = max(fams, key=lambda d: d["kernel_ms_per_step"]) if fams else None
     line = dict(
         metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=1e3 * t_dev / args.steps, higher_is_better=False, scaling="strong" if sharded else "weak", vs_baseline=None,
@@ -325,9 +337,17 @@ def run_b200(args):
                    factor_ms=fac_ms, factor_tflops=alg["factor"] / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else None,
                    assemble_plus_factor_tflops=(alg["assemble"] + alg["factor"]) / ((asm_ms + fac_ms) * 1e-3) / 1e12
                    if asm_ms + fac_ms > 0 else None),
-        roofline=dict(bound="tensor", kernel="dgemm_dmma_kernel (FP64 DMMA GEMM: SVD panel products, congruences, SYRK, TRSM)",
-                      achieved=achieved, peak=peak.value, unit="TFLOP/s", frac=achieved / peak.value if peak.value else None,
-                      traffic=None, launches_profiled=int(nl.value), kernel_ms_per_step=ms.value / prof_steps,
+        roofline=dict(bound="tensor", kernel=dom["kernel"] if dom else None,
+                      achieved=dom["achieved"] if dom else None, peak=peak.value, unit="TFLOP/s",
+                      frac=dom["achieved"] / peak.value if dom and peak.value else None,
+                      # DRAM bytes per launch from the ncu --set full capture of the same shape (profiles/r1c_svd_round_ncu_full.csv:
+                      # 212.7 MB read + 161.1 MB written; algorithmic: 200 MB read + 200 MB written incl. padding rows)
+                      traffic=373.8e6 if dom and dom["kernel"].startswith("panel_rotate") and args.workload == "C2" else None,
+                      launches_profiled=dom["launches"] if dom else 0, kernel_ms_per_step=dom["kernel_ms_per_step"] if dom else None,
+                      avg_launch_us=dom["avg_launch_us"] if dom else None,
+                      algorithmic_flops_per_launch=dom["algorithmic_flops_per_launch"] if dom else None,
+                      all_dmma_kernels=dict(achieved=achieved, launches=int(nl.value), kernel_ms_per_step=ms.value / prof_steps),
+                      by_kernel=fams,
                       peak_source="measured in this run: register-resident mma.sync.m8n8k4.f64 loop on all SMs "
                                   "(MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.4 TFLOP/s)"),
         stats=s.stats(),

@@ -30,7 +30,9 @@ int32_t lrn_dbg_batched_lambda_min(int32_t count, int32_t m, const double* mats,
 int32_t lrn_dbg_peak(int32_t kind, double* value);
 
 /* per-launch timing of the DMMA GEMM kernel (roofline bookkeeping of bench.py): mode 1 starts recording one CUDA-event pair
- * per launch on the launching stream, mode 0 stops and returns total kernel milliseconds, algorithmic flops and launches */
+ * per launch on the launching stream, mode 0 stops and returns total kernel milliseconds, algorithmic flops and launches;
+ * modes 10 / 11 / 12 return the same totals of the last stopped profile for the cp.async kernel / the TMA-fed kernel / the
+ * block-Jacobi panel-rotation kernel alone */
 int32_t lrn_dbg_gemm_profile(int32_t mode, double* ms, double* flops, int64_t* launches);
 
 #ifdef __cplusplus

@@ -416,7 +416,9 @@ __global__ void __launch_bounds__(288) panel_rotate_kernel(const PanelRotatePara
 std::atomic<long long> g_launches{0};
 
 // optional per-launch profiling (bench roofline): CUDA events around every DMMA GEMM launch on its own stream
-struct ProfRec { cudaEvent_t a, b; double flops; };
+struct ProfRec { cudaEvent_t a, b; double flops; int fam = 0; };   // fam: 0 cp.async kernel, 1 TMA-fed kernel, 2 panel rotation
+double g_fam_ms[3] = {0, 0, 0}, g_fam_flops[3] = {0, 0, 0};
+long long g_fam_n[3] = {0, 0, 0};
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 constexpr size_t PROF_CAP = 60000;
@@ -512,6 +514,7 @@ void launch_bulk(const GemmParams& p, cudaStream_t st) {
     LRN_CHECK_LAUNCH();
     if (prof) {
         LRN_CUDA(cudaEventRecord(rec.b, st));
+        rec.fam = 1;
         g_prof.push_back(rec);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -543,6 +546,7 @@ void panel_rotate(const PanelRotateParams& p, cudaStream_t st) {
     LRN_CHECK_LAUNCH();
     if (prof) {
         LRN_CUDA(cudaEventRecord(rec.b, st));
+        rec.fam = 2;
         g_prof.push_back(rec);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -606,12 +610,23 @@ void gemm_profile(int mode, double* ms, double* flops, long long* launches) {
         g_prof_on = true;
         return;
     }
+    if (mode >= 10 && mode <= 12) {          // per-kernel totals of the last stopped profile
+        const int f = mode - 10;
+        if (ms) *ms = g_fam_ms[f];
+        if (flops) *flops = g_fam_flops[f];
+        if (launches) *launches = g_fam_n[f];
+        return;
+    }
     g_prof_on = false;
     LRN_CUDA(cudaDeviceSynchronize());
     double t = 0.0, f = 0.0;
+    for (int k = 0; k < 3; k++) { g_fam_ms[k] = 0.0; g_fam_flops[k] = 0.0; g_fam_n[k] = 0; }
     for (auto& r : g_prof) {
         float e = 0.f;
-        if (cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) { t += e; f += r.flops; }
+        if (cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) {
+            t += e; f += r.flops;
+            g_fam_ms[r.fam] += e; g_fam_flops[r.fam] += r.flops; g_fam_n[r.fam]++;
+        }
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     if (ms) *ms = t;
