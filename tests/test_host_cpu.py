@@ -115,3 +115,22 @@ def test_generators_shapes(pkg):
     n, bs, c, body = pkg.problems.large_schur(20, 60, 3)
     cnt = np.bincount(body[body[:, 0] > 0][:, 0].astype(int))[1:]
     assert n == 60 and (cnt >= 1).all() and cnt.max() <= 15
+
+
+def test_full_size_checker_matches_oracle_assembly(pkg):
+    """The sampled-entry checker of the full-size GPU test (tests/test_gpu_solver.py::schur_entry_ref, the defining formula
+    tr(A_j W A_k W) of src/makeBBBB.jl:39-64) agrees with the oracle's Schur assembly on a small instance of the same family."""
+    import importlib.util
+    from oracle import loraine_oracle as lo, sdpa_io
+    spec = importlib.util.spec_from_file_location("tgs", os.path.join(os.path.dirname(__file__), "test_gpu_solver.py"))
+    tgs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tgs)
+    arrays = pkg.problems.large_schur(m=30, n=200, seed=3)
+    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=0, kappa=8)
+    rng = np.random.default_rng(1)
+    Q = rng.standard_normal((30, 30))
+    W = Q @ Q.T / 30 + np.eye(30)
+    H = lo.makeBBBBs(md, [W])
+    AA = md.AA[0].tocsr()
+    err = max(abs(tgs.schur_entry_ref(AA, W, j, k) - H[max(j, k), min(j, k)]) for j in range(0, 200, 7) for k in range(0, 200, 11))
+    assert err <= 1e-12 * np.abs(H).max()
