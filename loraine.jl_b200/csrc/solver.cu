@@ -557,6 +557,9 @@ int32_t lrn_destroy(lrn_handle_t h) {
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->evpool) cudaEventDestroy(e);
     cudaStream_t st = h->st;
+    for (auto& s_ : h->side) if (s_) { cudaStreamSynchronize(s_); cudaStreamDestroy(s_); }
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    for (auto& e : h->evJoin) if (e) cudaEventDestroy(e);
     delete h;
     if (st) cudaStreamDestroy(st);
     return LRN_OK;
@@ -1056,12 +1059,36 @@ int32_t lrn_dimacs(lrn_handle_t h, double* err6, double* by_out, double* trCX_ou
             R.dot_mat(st, B.m, B.m, B.Rd.p(), B.ld, B.Rd.p(), B.ld, 16 + 4 * i, false);
             R.dot_mat(st, B.m, B.m, B.S.p(), B.ld, B.X.p(), B.ld, 16 + 4 * i + 1, false);
             R.dot_mat(st, B.m, B.m, B.C.p(), B.C.ld, B.X.p(), B.ld, 16 + 4 * i + 2, false);
+        }
+        {
             // eigmin(X), eigmin(S) only enter as max(0, -eigmin): a successful Cholesky proves eigmin > 0; the factors
-            // are kept for the next prepare_W (X and S do not change in between)
-            LRN_CUDA(cudaMemcpyAsync(B.LX.p(), B.X.p(), B.X.bytes(), cudaMemcpyDeviceToDevice, st));
-            cholesky_lower(B.LX.p(), B.m, B.ld, B.cholX, st);
-            LRN_CUDA(cudaMemcpyAsync(B.LS.p(), B.S.p(), B.S.bytes(), cudaMemcpyDeviceToDevice, st));
-            cholesky_lower(B.LS.p(), B.m, B.ld, B.cholS, st);
+            // are kept for the next prepare_W (X and S do not change in between).  The 2 nlmi factorisations are independent
+            // and, for small blocks, latency-bound single-CTA-group kernels: multi-block problems spread them over side
+            // streams (fork / join with events) so that they overlap.
+            const bool fan = h->nlmi >= 4;
+            if (fan && !h->side[0]) {
+                for (auto& s_ : h->side) LRN_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+                LRN_CUDA(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+                for (auto& e : h->evJoin) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            if (fan) {
+                LRN_CUDA(cudaEventRecord(h->evFork, st));
+                for (auto& s_ : h->side) LRN_CUDA(cudaStreamWaitEvent(s_, h->evFork, 0));
+            }
+            for (int i = 0; i < h->nlmi; i++) {
+                Block& B = h->blk[i];
+                cudaStream_t sx = fan ? h->side[(2 * i) % lrn_solver::NSIDE] : st;
+                cudaStream_t ss = fan ? h->side[(2 * i + 1) % lrn_solver::NSIDE] : st;
+                LRN_CUDA(cudaMemcpyAsync(B.LX.p(), B.X.p(), B.X.bytes(), cudaMemcpyDeviceToDevice, sx));
+                cholesky_lower(B.LX.p(), B.m, B.ld, B.cholX, sx);
+                LRN_CUDA(cudaMemcpyAsync(B.LS.p(), B.S.p(), B.S.bytes(), cudaMemcpyDeviceToDevice, ss));
+                cholesky_lower(B.LS.p(), B.m, B.ld, B.cholS, ss);
+            }
+            if (fan)
+                for (int k = 0; k < lrn_solver::NSIDE; k++) {
+                    LRN_CUDA(cudaEventRecord(h->evJoin[k], h->side[k]));
+                    LRN_CUDA(cudaStreamWaitEvent(st, h->evJoin[k], 0));
+                }
         }
         if (h->nlin > 0) {
             R.min_ratio(st, h->nlin, h->x_lin.p, nullptr, 2, false);

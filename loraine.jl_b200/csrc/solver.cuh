@@ -80,6 +80,10 @@ struct lrn_solver {
     lrn::Reducer red;
     lrn::LanczosWork lan;
     cudaStream_t st = nullptr;
+    // side streams for independent per-block work of multi-block problems (fork / join around the loop with events)
+    static constexpr int NSIDE = 4;
+    cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evFork = nullptr, evJoin[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     // timers
     std::vector<lrn::PhaseEvt> pending;
