@@ -631,13 +631,33 @@ static void gemm_sym(cudaStream_t st, bool ta, bool tb, int m, const double* A, 
 // Sparse data: delS = Rd - M with a sparse M = mat(AA' dely), so G' delS G = G' Rd G - G' (M G).  G' Rd G is formed once per
 // iteration (Rd and G are fixed between lrn_residuals / lrn_prepare_W calls); M G is a gather product.
 static bool use_rdb(const Block& B) { return B.sp.sparse_ok && (double)B.sp.npos <= 0.05 * (double)B.m * B.m; }
-static void ensure_rdb(lrn_solver* h, Block& B) {
+static void ensure_rdb(lrn_solver* h, Block& B, cudaStream_t st) {
     if (B.rdb_valid) return;
     const int m = B.m, ld = B.ld;
-    if (!B.RdB.p()) B.RdB.init(m, m);
-    gemm_nn(h->st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
-    gemm_sym(h->st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.RdB.p(), B.RdB.ld);
+    if (!B.RdB.p()) {
+        LRN_CUDA(cudaStreamSynchronize(st));       // DevBuf allocation synchronises the device anyway; keep the order explicit
+        B.RdB.init(m, m);
+    }
+    gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
+    gemm_sym(st, true, false, m, B.G.p(), ld, B.T1.p(), ld, B.RdB.p(), B.RdB.ld);
     B.rdb_valid = true;
+}
+
+// fork / join of the side streams around a loop over independent PSD blocks
+static void side_fork(lrn_solver* h) {
+    if (!h->side[0]) {
+        for (auto& s_ : h->side) LRN_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+        LRN_CUDA(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+        for (auto& e : h->evJoin) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    LRN_CUDA(cudaEventRecord(h->evFork, h->st));
+    for (auto& s_ : h->side) LRN_CUDA(cudaStreamWaitEvent(s_, h->evFork, 0));
+}
+static void side_join(lrn_solver* h) {
+    for (int k = 0; k < lrn_solver::NSIDE; k++) {
+        LRN_CUDA(cudaEventRecord(h->evJoin[k], h->side[k]));
+        LRN_CUDA(cudaStreamWaitEvent(h->st, h->evJoin[k], 0));
+    }
 }
 
 // ---- hot path -------------------------------------------------------------------------------------------------------
@@ -691,8 +711,13 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
                 h->stat_svd_sweeps = svd_block_jacobi(B.T1.p(), B.ld, B.m, B.T2.p(), B.ld, nullptr, 0, B.D.p, B.svd, svd_tol, 30, st);
             }
         }
-        for (auto& B : h->blk) {
+        const bool fanw = h->nlmi >= 4;          // independent per-block post-processing chains -> side streams
+        if (fanw) side_fork(h);
+        cudaStream_t st_main = st;
+        for (int ib = 0; ib < h->nlmi; ib++) {
+            Block& B = h->blk[ib];
             const int m = B.m, ld = B.ld;
+            cudaStream_t st = fanw ? h->side[ib % lrn_solver::NSIDE] : st_main;
             vec_op(st, m, VEC_RSQRT, B.dm12.p, B.D.p, nullptr);
             vec_op(st, m, VEC_POW_M32, B.dm32.p, B.D.p, nullptr);
             // G = L_X V D^{-1/2} = L_S^{-T} (U D) D^{-1/2}   (CC V = U D with CC = L_S' L_X)   (src/prepare_W.jl:60)
@@ -710,6 +735,7 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
             LRN_CUDA(cudaMemcpyAsync(B.DDsi.p, B.dm12.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
             B.ud_valid = true;        // T2 = U D and LS stay intact until the next call that uses the scratch matrices
         }
+        if (fanw) side_join(h);
         if (h->nlin > 0) vec_op(st, h->nlin, VEC_RECIP, h->si_lin.p, h->s_lin.p, nullptr);
         return LRN_OK;
     });
@@ -837,7 +863,7 @@ int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
             const int m = B.m, ld = B.ld;
             // h += AA * vec(G (G' Rd G + diag(D) - diag(sigma mu ./ D) - RNT) G')      (src/predictor_corrector.jl:186)
             if (use_rdb(B)) {
-                ensure_rdb(h, B);
+                ensure_rdb(h, B, st);
                 LRN_CUDA(cudaMemcpyAsync(B.T2.p(), B.RdB.p(), B.RdB.bytes(), cudaMemcpyDeviceToDevice, st));
             } else {
                 gemm_nn(st, m, m, m, 1.0, B.Rd.p(), ld, B.G.p(), ld, 0.0, B.T1.p(), ld);
@@ -912,15 +938,21 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
         Phase ph(h, LRN_T_FIND_STEP);
         cudaStream_t st = h->st;
         const double sm = sigma * mu;
+        // multi-block problems whose blocks all go to the batched lambda_min kernel have no host synchronisation inside the
+        // loop: the independent per-block chains of small kernels are spread over the side streams
+        bool fan = h->nlmi >= 4 && h->eig_small.size() == (size_t)h->nlmi;
+        if (fan) side_fork(h);
+        cudaStream_t st_main = st;
         for (int i = 0; i < h->nlmi; i++) {
             Block& B = h->blk[i];
             const int m = B.m, ld = B.ld;
+            cudaStream_t st = fan ? h->side[i % lrn_solver::NSIDE] : st_main;
             // delS = Rd - mat(AA' dely)                                        (src/predictor_corrector.jl:252)
             LRN_CUDA(cudaMemcpyAsync(B.dS.p(), B.Rd.p(), B.Rd.bytes(), cudaMemcpyDeviceToDevice, st));
             sp_scatter_ATy(st, B.sp, h->dely.p, -1.0, B.dS.p(), ld);
             // delSb = G' delS G                                                (:263)
             if (use_rdb(B)) {
-                ensure_rdb(h, B);
+                ensure_rdb(h, B, st);
                 sp_pos_values(st, B.sp, h->dely.p);
                 sp_M_times_W(st, B.sp, B.G.p(), ld, B.T1.p(), ld);                      // T1 = M G
                 LRN_CUDA(cudaMemcpyAsync(B.T2.p(), B.RdB.p(), B.RdB.bytes(), cudaMemcpyDeviceToDevice, st));
@@ -968,6 +1000,7 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
                 beta[i] = steplen(lambda_min(h, B.T1.p(), m, ld), tau);
             }
         }
+        if (fan) side_join(h);
         if (!h->eig_small.empty()) {
             Phase pe(h, LRN_T_EIGMIN);
             const int cnt = 2 * (int)h->eig_small.size();
