@@ -37,3 +37,13 @@ for name in ("theta1", "control1", "tru3", "vib3", "maxG11"):
                         oracle_obj_trace=np.array([t["obj"] for t in s.trace]),
                         oracle_dimacs_trace=np.array([t["dimacs"] for t in s.trace]), **extra)
     print(name, s.iter, s.primal_obj, s.status)
+
+# Larger instances of the reference's data directory: end-to-end oracle results only (the oracle needs 9 min for tru9,
+# 31 min for vib9 and 1.5 min for thetaG11 on 16 cores; thetaG11 is the reference's kit = 1 use case, SDPLIB optimum 400).
+for name, extra in (("tru9", {}), ("vib9", {}), ("thetaG11", dict(kit=1))):
+    n, bs, c, body = sdpa_io.parse_sdpa(os.path.join(DATA, name + ".dat-s"))
+    s = lo.solve_raw(sdpa_io.raw_from_sdpa_arrays(n, bs, c, body), dict(OPTS, **extra))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), n=n, bs=np.array(bs), c=c, body=body, oracle_iters=s.iter,
+                        oracle_obj=s.primal_obj, oracle_dual_obj=s.dual_obj, oracle_cg_iters=getattr(s, "cg_iter_tot", 0))
+    print(name, s.iter, s.primal_obj, s.status)
+

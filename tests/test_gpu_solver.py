@@ -547,3 +547,25 @@ def test_full_size_C5_properties(pkg):
     rhs = torch.from_numpy(g.get_array("RHS")).to(dev)
     assert float(torch.linalg.norm(Ht @ dely - rhs) / torch.linalg.norm(rhs)) <= 1e-9
     g.close()
+
+
+@pytest.mark.parametrize("name,extra", [("tru9", {}), ("vib9", {}), ("thetaG11", dict(kit=1))])
+def test_end_to_end_reference_data_large(pkg, golden_dir, name, extra):
+    """The larger instances shipped in the reference's examples/data (tru9 / vib9: PSD blocks + a 6480-entry LP block,
+    n_var = 3240; thetaG11: m = 801, n_var = 2401, the kit = 1 use case) with the options of examples/solve_sdpa.jl:
+    objective and iteration count against the oracle's solve stored in the fixture (thetaG11 also: SDPLIB optimum 400)."""
+    z, arrays = golden(golden_dir, name)
+    opt = pkg.Optimizer()
+    for k, v in dict(OPTS_SDPA, **extra).items():
+        opt.set_attribute(k, v)
+    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
+    opt.optimize()
+    s = opt.solver
+    assert s.status == 1
+    ref_obj, ref_it = float(z["oracle_obj"]), int(z["oracle_iters"])
+    assert abs(s.primal_obj - ref_obj) <= 2e-6 * (1 + abs(ref_obj))
+    assert abs(s.iter - ref_it) <= 1
+    if name == "thetaG11":
+        assert abs(s.primal_obj - 400.0) <= 1e-3
+        assert abs(s.cg_iter_tot - int(z["oracle_cg_iters"])) <= 0.2 * int(z["oracle_cg_iters"])
+    s.close()
