@@ -1,6 +1,8 @@
-// Blocked right-looking Cholesky: 64x64 diagonal blocks are factored AND inverted by one CTA in shared memory; the panel
-// TRSM is two DMMA GEMMs per 64-column block (using the inverted diagonal blocks); the trailing update is a lower-only
-// DMMA SYRK-shaped GEMM with K = panel width (64..512, recursion keeps the bulk of the flops in large-K updates).
+// Blocked right-looking Cholesky with one-step look-ahead on two streams.  A panel's diagonal block (<= 512) is factored by
+// one cooperative kernel: 64x64 blocks are factored AND inverted in registers / shared memory, the full inverse of the
+// diagonal block is assembled, and the rows below are solved with ONE DMMA GEMM against it; the trailing update is a
+// lower-only SYRK-shaped product with K = panel width on the TMA-fed kernel.  Triangular solves advance 256 unknowns per
+// step through pre-built inverses of the 256x256 diagonal blocks (see chol_solve).
 #include "chol.cuh"
 #include "gemm.cuh"
 #include <cooperative_groups.h>

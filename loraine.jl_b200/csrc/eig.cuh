@@ -1,8 +1,9 @@
 // Symmetric eigen / SVD machinery of the NT-scaling and step-length code paths.
 //   * jacobi_eig_small : batched two-sided Jacobi eigensolver for symmetric matrices up to 64x64 (one CTA each, smem).
-//   * svd_block_jacobi : one-sided (Hestenes) block Jacobi SVD of a dense m x m matrix; column-block pairs are
-//                        diagonalised through their 64x64 Gram matrices; all O(m^3) work is DMMA GEMM.
-//                        Replaces FameSVD.fsvd at src/prepare_W.jl:42.
+//   * svd_block_jacobi : one-sided (Hestenes) block Jacobi SVD of a dense m x m matrix; column-block pairs are rotated
+//                        through their 64x64 Gram matrices (only the 32x32 cross block is recomputed per round, the
+//                        diagonal blocks travel with the column blocks); all O(m^3) work is DMMA (cross Gram GEMM,
+//                        persistent TMA-fed panel rotation).  Replaces FameSVD.fsvd at src/prepare_W.jl:42.
 //   * lanczos_extreme  : extreme eigenpairs of a dense symmetric matrix by Lanczos with full re-orthogonalisation.
 //                        Replaces `eigmin` (src/predictor_corrector.jl:272,285; src/Solvers.jl:503,505) and the
 //                        `eigen(W)` calls of the preconditioners (src/Solvers.jl:642,706), which only use the erank
