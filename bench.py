@@ -190,6 +190,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's own messages (version banner, INFO) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as g
     pkg = g.load_package()
