@@ -159,6 +159,14 @@ int32_t lrn_set_option(lrn_handle_t h, const char* name, double value);
 /* diagnostic counters of the last calls: [0] svd sweeps, [1] lanczos iterations (sum), [2] lanczos not converged count */
 int32_t lrn_stats(lrn_handle_t h, int64_t* out3);
 
+/* ---- multi-GPU, in-process: ONE host thread drives `ngpus` devices through one handle (the unchanged
+ * single-process Loraine.Optimizer, src/MOI_wrapper.jl:136-140, can use the whole box).  The library creates one solver per
+ * device (devices[r], or 0..ngpus-1 when devices is NULL) and their NCCL communicators with ncclCommInitAll; every other
+ * entry point accepts the returned handle unchanged and fans the call out to the devices (Schur rows and the Cholesky
+ * factorisation are sharded block-cyclically, the m x m work of the iteration is replicated).  ngpus <= 0: all devices. ---- */
+int32_t lrn_create_multi(lrn_handle_t* out, int64_t n_var, int64_t nlmi, const int64_t* msizes, int64_t nlin,
+                         const lrn_options_t* opt, int32_t ngpus, const int32_t* devices);
+
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) ---- */
 /* unique id: 128 bytes generated on rank 0 with lrn_dist_unique_id and broadcast by the host (torch.distributed / MPI) */
 int32_t lrn_dist_unique_id(void* out128);

@@ -4,6 +4,7 @@
 #ifndef LORAINE_B200_DEBUG_H
 #define LORAINE_B200_DEBUG_H
 #include <stdint.h>
+#include "loraine_b200.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -34,6 +35,17 @@ int32_t lrn_dbg_peak(int32_t kind, double* value);
  * modes 10 / 11 / 12 return the same totals of the last stopped profile for the cp.async kernel / the TMA-fed kernel / the
  * block-Jacobi panel-rotation kernel alone */
 int32_t lrn_dbg_gemm_profile(int32_t mode, double* ms, double* flops, int64_t* launches);
+
+/* test hook: give a single-GPU handle the Schur-row ownership of `rank` out of `world` (row blocks of `block_rows` rows, 0 =
+ * the library's default for n_var) WITHOUT a communicator: lrn_schur_assemble then fills only the owned row blocks, so a test
+ * on one GPU can check that the shards of all ranks add up to the full matrix.  lrn_schur_factor refuses to run in that state. */
+int32_t lrn_dbg_set_shard(lrn_handle_t h, int32_t rank, int32_t world, int32_t block_rows);
+/* relative Frobenius distance ||A_a - A_b||_F / ||A_b||_F over the LOWER triangles of the n_var x n_var Schur matrices
+ * (which = LRN_ARR_H) or Cholesky factors (LRN_ARR_L) of two handles living on the same device; computed on the device
+ * (bench.py's dist_parity: sharded handle against a single-GPU handle at n_var = 40000 without a 12.8 GB download) */
+int32_t lrn_dbg_compare(lrn_handle_t a, lrn_handle_t b, int32_t which, double* relerr);
+/* multi-GPU: sum the row-block shards of the Schur matrix over all ranks in place (collective; every rank calls) */
+int32_t lrn_dbg_gather_H(lrn_handle_t h);
 
 #ifdef __cplusplus
 }

@@ -255,12 +255,11 @@ constexpr int COOP_MAXN = 512;
 int pick_nb(int n) { return n > 8192 ? 512 : 256; }
 
 void potrf_launch_config() {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    once.run([&] {
         LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
         LRN_CUDA(cudaFuncSetAttribute(potrf_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
-        configured = true;
-    }
+    });
 }
 
 // factor a block of side n <= 512 with one launch; X (optional, n x n, ldx) receives the full inverse of the factor
@@ -507,6 +506,10 @@ __global__ void zero_upper_kernel(double* A, int n, int lda) {
 }
 
 }  // namespace
+
+void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int ldx, int* info, int base, cudaStream_t st) {
+    potrf_small(Akk, lda, w, dinv, X, ldx, info, base, st);
+}
 
 void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
                     int ldp, cudaStream_t st) {

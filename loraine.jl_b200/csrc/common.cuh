@@ -46,6 +46,21 @@ struct CudaError : std::runtime_error {
         }                                                                                           \
     } while (0)
 
+// Runs `f` once per CUDA device (function attributes such as the dynamic shared-memory opt-in are per device; a process may
+// drive several devices, one handle each).  Thread-safe for concurrent callers on different devices.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    template <typename F>
+    void run(F&& f) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (mask.load(std::memory_order_acquire) & bit) return;
+        f();
+        mask.fetch_or(bit, std::memory_order_release);
+    }
+};
+
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 

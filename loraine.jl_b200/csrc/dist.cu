@@ -3,6 +3,7 @@
 #include "chol.cuh"
 #include "gemm.cuh"
 #include <dlfcn.h>
+#include <algorithm>
 
 namespace lrn {
 
@@ -17,6 +18,7 @@ const NcclApi& nccl_api() {
             auto sym = [&](const char* n) { return dlsym(hnd, n); };
             api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
             api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
             api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
             api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
             api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
@@ -31,81 +33,176 @@ const NcclApi& nccl_api() {
     return api;
 }
 
-namespace {
-__global__ void k_pack_panel(const double* __restrict__ A, int lda, int rows, int w, double* __restrict__ P, int ldp, int unpack) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (i >= rows || j >= w) return;
-    if (unpack) const_cast<double*>(A)[(size_t)j * lda + i] = P[(size_t)j * ldp + i];
-    else P[(size_t)j * ldp + i] = A[(size_t)j * lda + i];
+DistCtx::~DistCtx() {
+    if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
+    comm = nullptr;
 }
-__global__ void k_max_int(int* a, const int* b) { if (*b != 0 && (*a == 0 || *b < *a)) *a = *b; }
+
+namespace {
+// recv[r][z] (pw x pw, ld pw) holds row block g = first_r + z * world of column panel p as solved by rank r; store every
+// block at its place in L.  grid = (row chunks, w columns, world * maxcnt slots)
+__global__ void k_unpack_blocks(const double* __restrict__ recv, double* __restrict__ L, int lda, int n, int c0, int w, int pw, int p,
+                                int world, int maxcnt, int nblk) {
+    const int slot = blockIdx.z, r = slot / maxcnt, z = slot - r * maxcnt;
+    const int first = p + ((r - p % world + world) % world);
+    const int g = first + z * world;
+    if (g >= nblk) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int row = g * pw + i;
+    if (i >= pw || row >= n || j >= w) return;
+    L[(size_t)(c0 + j) * lda + row] = recv[((size_t)slot * pw + j) * pw + i];
+}
+__global__ void k_min_nonzero(int* a, const int* b, int cnt) {
+    int best = 0;
+    for (int r = 0; r < cnt; r++) if (b[r] != 0 && (best == 0 || b[r] < best)) best = b[r];
+    *a = best;
+}
+__global__ void k_copy_block(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i < rows && j < cols) dst[(size_t)j * ldd + i] = src[(size_t)j * lds + i];
+}
+
+// first row block >= p owned by `rank`, and how many of its blocks are >= p
+inline int first_block(int p, int rank, int world) { return p + ((rank - p % world + world) % world); }
+inline int count_blocks(int p, int rank, int world, int nblk) {
+    const int f = first_block(p, rank, world);
+    return f >= nblk ? 0 : (nblk - 1 - f) / world + 1;
+}
+
+// C[rows of my blocks g >= gmin, cols [cbeg, cend)] (+)= alpha * f(A[rows, 0:K] * Bm[cbeg:cend, 0:K]^T); `lower` clips every row
+// block at its own diagonal block (staircase).  Whole blocks go through one strided-batch launch, a partial last block through
+// a second one.
+void row_block_gemm(cudaStream_t st, int n, int pw, int rank, int world, int gmin, const double* A, int lda, const double* Bm,
+                    int ldb, double* C, int ldc, int cbeg, int cend, int K, double alpha, double beta, int mode, bool lower) {
+    const int nblk = (int)cdiv(n, pw);
+    const int f = first_block(gmin, rank, world);
+    if (f >= nblk || cend <= cbeg) return;
+    const int cnt = (nblk - 1 - f) / world + 1;
+    const int glast = f + (cnt - 1) * world;
+    const bool last_partial = (glast == nblk - 1) && (n - glast * pw < pw);
+    const int nfull = last_partial ? cnt - 1 : cnt;
+    auto base = [&](GemmParams& g) {
+        g.B = Bm + cbeg; g.ldb = ldb; g.lda = lda; g.ldc = ldc; g.K = K; g.transB = true;
+        g.alpha = alpha; g.beta = beta; g.mode = mode; g.lower = lower ? 1 : 0; g.col0 = cbeg;
+    };
+    if (nfull > 0) {
+        GemmParams g;
+        base(g);
+        const int gl = f + (nfull - 1) * world;
+        g.A = A + (size_t)f * pw; g.C = C + (size_t)cbeg * ldc + (size_t)f * pw;
+        g.M = pw; g.N = (lower ? std::min(cend, (gl + 1) * pw) : cend) - cbeg;
+        g.batch = nfull; g.sA = (long long)world * pw; g.sC = (long long)world * pw; g.sB = 0;
+        g.row0 = f * pw; g.row0z = (long long)world * pw;
+        if (g.N > 0) gemm(g, st);
+    }
+    if (last_partial) {
+        GemmParams g;
+        base(g);
+        g.A = A + (size_t)glast * pw; g.C = C + (size_t)cbeg * ldc + (size_t)glast * pw;
+        g.M = n - glast * pw; g.N = cend - cbeg; g.row0 = glast * pw;
+        gemm(g, st);
+    }
+}
 }  // namespace
 
 void dist_allreduce_sum(double* buf, size_t count, DistCtx& ctx, cudaStream_t st) {
     LRN_NCCL(nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx.comm, st));
 }
 
-void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int pw, DevBuf<double>& panelbuf, cudaStream_t st) {
+void syrk_sq_row_blocks(const double* BG, int ldbg, int n, int K, double* H, int ldh, int rank, int world, int pw, cudaStream_t st) {
+    row_block_gemm(st, n, pw, rank, world, 0, BG, ldbg, BG, ldbg, H, ldh, 0, n, K, 1.0, 1.0, 1, true);
+}
+
+void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int pw, cudaStream_t st) {
     work.tinv_for = nullptr;   // the triangular solves rebuild their diagonal-block inverses from the new factor
     work.ensure(n);
-    LRN_REQUIRE(pw % CHOL_DB == 0, "panel width must be a multiple of 64");
-    const int npan = (int)cdiv(n, pw), ldp = pad_ld(n);
-    const size_t ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
-    const size_t bufsz = (size_t)ldp * pw + ndmax + 8;
-    if (panelbuf.n < 2 * bufsz) panelbuf.alloc(2 * bufsz);
+    LRN_REQUIRE(pw % CHOL_DB == 0 && pw <= 512, "row block height must be a multiple of 64, at most 512");
+    LRN_REQUIRE(ctx.comm, "no NCCL communicator (lrn_dist_init)");
+    const int world = ctx.world, rank = ctx.rank;
+    const int nblk = (int)cdiv(n, pw);
+    const int maxcnt0 = (int)cdiv(nblk, world);
+    const size_t blk = (size_t)pw * pw, ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
+    if (ctx.xb.n < blk + ndmax) ctx.xb.alloc(blk + ndmax);
+    if (ctx.sendbuf.n < (size_t)maxcnt0 * blk) ctx.sendbuf.alloc((size_t)maxcnt0 * blk);
+    if (ctx.recvbuf.n < (size_t)maxcnt0 * blk * world) ctx.recvbuf.alloc((size_t)maxcnt0 * blk * world);
+    if (ctx.infos.n < (size_t)world) ctx.infos.alloc(world);
     ensure_aux(work);
-    cudaStream_t sp = work.aux;                     // panel stream: factor panel p+1 and broadcast it while `st` still
-    cudaEvent_t evStart = work.ev[0], evU = work.ev[1];   // applies the trailing updates of panel p (one-step look-ahead)
-    cudaEvent_t evB[2] = {work.ev[2], work.ev[3]}, evE[2] = {work.ev[4], work.ev[5]};
+    cudaStream_t sp = work.aux;                     // panel stream (high priority): diagonal block, broadcast, row solves, all-gather
+    cudaEvent_t evStart = work.ev[0], evU = work.ev[1], evB = work.ev[2];
     int* info = work.info_ptr();
     LRN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     LRN_CUDA(cudaEventRecord(evStart, st));
     LRN_CUDA(cudaStreamWaitEvent(sp, evStart, 0));
-    LRN_CUDA(cudaEventRecord(evU, st));
-    for (int p = 0; p < npan; p++) {
-        const int b = p & 1;
-        const int c0 = p * pw, w = (n - c0 < pw) ? (n - c0) : pw, rows = n - c0, owner = p % ctx.world;
-        double* buf = panelbuf.p + (size_t)b * bufsz;
-        double* Ap = A + (size_t)c0 * lda + c0;
+    double* X = ctx.xb.p;
+    double* xd = ctx.xb.p + blk;
+    for (int p = 0; p < nblk; p++) {
+        const int c0 = p * pw, w = std::min(pw, n - c0), owner = p % world;
         double* dk = work.dinv.p + (size_t)(c0 / CHOL_DB) * CHOL_DB * CHOL_DB;
         const int nd = (int)cdiv(w, CHOL_DB) * CHOL_DB * CHOL_DB;
-        double* dbuf = buf + (size_t)ldp * pw;
-        if (p >= 2) LRN_CUDA(cudaStreamWaitEvent(sp, evE[b], 0));      // buffer b was last read by the updates of step p-2
-        if (ctx.rank == owner) {
-            LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));                    // panel p has received the update of step p-1
-            cholesky_panel(Ap, rows, w, lda, dk, info, c0, work, buf, ldp, sp);   // factor + pack
-            LRN_CUDA(cudaMemcpyAsync(dbuf, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
+        // ---- panel chain of step p ------------------------------------------------------------------------------------
+        if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));             // column block p has received the update of step p-1
+        if (rank == owner) {
+            chol_diag_block(A + (size_t)c0 * lda + c0, lda, w, dk, X, pw, info, c0, sp);
+            LRN_CUDA(cudaMemcpyAsync(xd, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
         }
-        // one broadcast carries the panel and its inverse diagonal blocks (contiguous in buf)
-        LRN_NCCL(nccl_api().Broadcast(buf, buf, (size_t)ldp * pw + nd, ncclDouble, owner, ctx.comm, sp));
-        LRN_CUDA(cudaEventRecord(evB[b], sp));
-        LRN_CUDA(cudaStreamWaitEvent(st, evB[b], 0));
-        if (ctx.rank != owner) {                                          // every rank keeps the complete factor
-            dim3 grid((unsigned)cdiv(rows, 256), (unsigned)w);
-            k_pack_panel<<<grid, 256, 0, st>>>(Ap, lda, rows, w, buf, ldp, 1);
+        if (world > 1) LRN_NCCL(nccl_api().Broadcast(ctx.xb.p, ctx.xb.p, blk + ndmax, ncclDouble, owner, ctx.comm, sp));
+        if (rank != owner) LRN_CUDA(cudaMemcpyAsync(dk, xd, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
+        const int maxcnt = (int)cdiv(nblk - p, world);
+        if (p + 1 < nblk || world > 1) {
+            // my row blocks g > p of the panel:  send[z] = A[g rows, panel p] * X^T ; the owner's slot 0 is the diagonal block itself
+            const int f = first_block(p, rank, world), cnt = count_blocks(p, rank, world, nblk);
+            const int z0 = (rank == owner) ? 1 : 0;
+            if (rank == owner) {
+                dim3 grid((unsigned)cdiv(w, 256), (unsigned)w);
+                k_copy_block<<<grid, 256, 0, sp>>>(A + (size_t)c0 * lda + c0, lda, ctx.sendbuf.p, pw, w, w);
+                LRN_CHECK_LAUNCH();
+            }
+            if (cnt > z0) {
+                const int glast = f + (cnt - 1) * world;
+                const bool last_partial = (glast == nblk - 1) && (n - glast * pw < pw);
+                const int nfull = (last_partial ? cnt - 1 : cnt) - z0;
+                if (nfull > 0) {
+                    GemmParams g;
+                    g.A = A + (size_t)c0 * lda + (size_t)(f + z0 * world) * pw; g.lda = lda; g.sA = (long long)world * pw;
+                    g.B = X; g.ldb = pw; g.transB = true;
+                    g.C = ctx.sendbuf.p + (size_t)z0 * blk; g.ldc = pw; g.sC = (long long)blk;
+                    g.M = pw; g.N = w; g.K = w; g.batch = nfull;
+                    gemm(g, sp);
+                }
+                if (last_partial && glast > p) {
+                    GemmParams g;
+                    g.A = A + (size_t)c0 * lda + (size_t)glast * pw; g.lda = lda;
+                    g.B = X; g.ldb = pw; g.transB = true;
+                    g.C = ctx.sendbuf.p + (size_t)(cnt - 1) * blk; g.ldc = pw;
+                    g.M = n - glast * pw; g.N = w; g.K = w;
+                    gemm(g, sp);
+                }
+            }
+            const double* src = ctx.sendbuf.p;
+            if (world > 1) {
+                LRN_NCCL(nccl_api().AllGather(ctx.sendbuf.p, ctx.recvbuf.p, (size_t)maxcnt * blk, ncclDouble, ctx.comm, sp));
+                src = ctx.recvbuf.p;
+            }
+            dim3 grid((unsigned)cdiv(pw, 256), (unsigned)w, (unsigned)(world * maxcnt));
+            k_unpack_blocks<<<grid, 256, 0, sp>>>(src, A, lda, n, c0, w, pw, p, world, maxcnt, nblk);
             LRN_CHECK_LAUNCH();
-            LRN_CUDA(cudaMemcpyAsync(dk, dbuf, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
         }
-        auto update = [&](int q) {
-            const int q0 = q * pw, wq = (n - q0 < pw) ? (n - q0) : pw;
-            const double* Pq = buf + (q0 - c0);
-            gemm_nt(st, n - q0, wq, w, -1.0, Pq, ldp, Pq, ldp, 1.0, A + (size_t)q0 * lda + q0, lda);
-        };
-        if (p + 1 < npan && (p + 1) % ctx.world == ctx.rank) {            // next panel first, so that its owner can go on
-            update(p + 1);
-            LRN_CUDA(cudaEventRecord(evU, st));
-        }
-        for (int q = p + 2; q < npan; q++)
-            if (q % ctx.world == ctx.rank) update(q);
-        LRN_CUDA(cudaEventRecord(evE[b], st));
+        LRN_CUDA(cudaEventRecord(evB, sp));
+        LRN_CUDA(cudaStreamWaitEvent(st, evB, 0));
+        if (p + 1 >= nblk) break;
+        // ---- trailing update with panel p: next column block first (so that the panel chain of step p+1 can start) --------------
+        const double* P = A + (size_t)c0 * lda;                            // column panel p: rows are global
+        const int c1 = c0 + pw, c2 = std::min(n, c1 + pw);
+        row_block_gemm(st, n, pw, rank, world, p + 1, P, lda, P, lda, A, lda, c1, c2, w, -1.0, 1.0, 0, false);
+        LRN_CUDA(cudaEventRecord(evU, st));
+        if (c2 < n) row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c2, n, w, -1.0, 1.0, 0, true);
     }
-    // the first failing pivot index is known to the owner of that panel only: take the smallest non-zero over ranks
-    int* all = nullptr;
-    LRN_CUDA(cudaMalloc(&all, sizeof(int) * ctx.world));
-    LRN_NCCL(nccl_api().AllGather(info, all, 1, ncclInt32, ctx.comm, st));
-    for (int r = 0; r < ctx.world; r++) k_max_int<<<1, 1, 0, st>>>(info, all + r);
-    LRN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(all);
+    // the first failing pivot index is known to the owner of that block only: take the smallest non-zero over ranks
+    if (world > 1) {
+        LRN_NCCL(nccl_api().AllGather(info, ctx.infos.p, 1, ncclInt32, ctx.comm, st));
+        k_min_nonzero<<<1, 1, 0, st>>>(info, ctx.infos.p, world);
+        LRN_CHECK_LAUNCH();
+    }
 }
 
 }  // namespace lrn
@@ -129,6 +226,7 @@ int32_t lrn_dist_unique_id(void* out128) {
 
 int32_t lrn_dist_init(lrn_handle_t h, int32_t rank, int32_t world, const void* unique_id128) {
     if (!h || !unique_id128 || world < 1 || rank < 0 || rank >= world) return LRN_ERR_ARG;
+    if (h->group) { h->err = "lrn_dist_init: the handle already drives several GPUs in-process (lrn_create_multi)"; return LRN_ERR_STATE; }
     try {
         LRN_CUDA(cudaSetDevice(h->device));
         ncclUniqueId id;
@@ -137,6 +235,7 @@ int32_t lrn_dist_init(lrn_handle_t h, int32_t rank, int32_t world, const void* u
         ctx->rank = rank;
         ctx->world = world;
         LRN_NCCL(nccl_api().CommInitRank(&ctx->comm, world, id, rank));
+        if (h->nccl) delete static_cast<DistCtx*>(h->nccl);
         h->nccl = ctx;
         h->rank = rank;
         h->world = world;

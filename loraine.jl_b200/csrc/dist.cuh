@@ -9,6 +9,7 @@ namespace lrn {
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -23,14 +24,24 @@ const NcclApi& nccl_api();   // throws std::runtime_error when libnccl cannot be
 struct DistCtx {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    bool emulated = false;             // test hook: (rank, world) set without a communicator (assembly ownership only)
+    DevBuf<double> xb;                 // broadcast buffer: inverse of the current diagonal block + its 64 x 64 inverse blocks
+    DevBuf<double> sendbuf, recvbuf;   // solved row blocks of the current panel: mine / everybody's (ncclAllGather)
+    DevBuf<int> infos;                 // world pivot flags
+    ~DistCtx();
 };
 
 struct CholWork;
-// Distributed right-looking Cholesky, 1-D block-cyclic by column panels of width pw (panel p -> rank p % world).
-// On entry every rank holds its OWN panels of the lower triangle of A (other panels: don't care); on return every rank
-// holds the complete factor L and all inverse diagonal blocks (panels are broadcast with ncclBroadcast as they are
-// finished, the receivers store them), so triangular solves run replicated without further communication.
-void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int pw, DevBuf<double>& panelbuf, cudaStream_t st);
+// Distributed right-looking Cholesky, 1-D block-cyclic by ROW blocks of height pw (row block g -> rank g % world).
+// On entry every rank holds its OWN row blocks of the lower triangle of A (other rows: don't care).  Step p: the owner of
+// diagonal block p factors it and broadcasts the inverse of the factor (<= 2 MB); every rank solves its own rows of column
+// panel p with one batched DMMA GEMM; the solved row blocks are exchanged with ONE ncclAllGather (each rank sends 1/world of
+// the panel) and stored in place, so every rank ends with the complete factor L (triangular solves run replicated); every
+// rank then updates its own row blocks of the trailing matrix (strided-batch lower-staircase GEMM on the TMA-fed kernel).
+// The panel chain of step p+1 runs on a high-priority stream while the main stream still applies the update of step p.
+void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int pw, cudaStream_t st);
+// Schur assembly, rank-one path, for the row blocks of one rank:  H[rows g, 0:(g+1) pw] += ((BG)(BG)').^2 (lower staircase)
+void syrk_sq_row_blocks(const double* BG, int ldbg, int n, int K, double* H, int ldh, int rank, int world, int pw, cudaStream_t st);
 // in-place sum of a device buffer over all ranks
 void dist_allreduce_sum(double* buf, size_t count, DistCtx& ctx, cudaStream_t st);
 

@@ -743,24 +743,15 @@ void batched_lambda_min(double* const* mats, const int* ms, const int* lds, int 
 
 void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st) {
     LRN_REQUIRE(p.n >= 1 && p.n <= EN, "jacobi_eig_small handles n <= 64");
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;               // the shared-memory opt-ins are per-device attributes
+    once.run([&] {
         LRN_CUDA(cudaFuncSetAttribute(jacobi_eig64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
-        configured = true;
-    }
+        LRN_CUDA(cudaFuncSetAttribute(jacobi_cross64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
+        LRN_CUDA(cudaFuncSetAttribute(jacobi_cross64_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(EN * ELD * sizeof(double))));
+    });
     if (p.cross_only && p.n == EN && p.relative && p.max_sweeps == 1 && !p.evals && !p.minval && !p.sort_desc) {
-        static bool configured_x = false;
-        if (!configured_x) {
-            LRN_CUDA(cudaFuncSetAttribute(jacobi_cross64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIG_SMEM));
-            configured_x = true;
-        }
         if (p.dg_in && p.dg_out && p.V) {
-            static bool configured_r = false;
-            if (!configured_r) {
-                LRN_CUDA(cudaFuncSetAttribute(jacobi_cross64_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)(EN * ELD * sizeof(double))));
-                configured_r = true;
-            }
             jacobi_cross64_reg_kernel<<<p.batch, 1024, EN * ELD * sizeof(double), st>>>(p);
             LRN_CHECK_LAUNCH();
             return;

@@ -108,9 +108,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     extern __shared__ __align__(16) double smem[];
 
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    if (p.lower && (p.row0 + m0 + BM - 1 < p.col0 + n0)) return;
     const int z = blockIdx.z;
     const int z1 = z / p.batch2, z2 = z - z1 * p.batch2;
+    if (p.lower && (p.row0 + (long long)z1 * p.row0z + m0 + BM - 1 < p.col0 + n0)) return;
     const double* __restrict__ A = p.A + (size_t)z1 * p.sA + (size_t)z2 * p.sA2;
     const double* __restrict__ B = p.B + (size_t)z1 * p.sB + (size_t)z2 * p.sB2;
     double* __restrict__ C = p.cblkmap ? p.C : p.C + (size_t)z1 * p.sC + (size_t)z2 * p.sC2;
@@ -241,7 +241,8 @@ template <bool TB>
 __global__ void __launch_bounds__(288, 1) dgemm_dmma_bulk_kernel(const GemmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
-    if (p.lower && (m0 + 127 < n0)) return;
+    const int z = blockIdx.z;                  // strided batch (row blocks of a block-cyclic distribution)
+    if (p.lower && (p.row0 + (long long)z * p.row0z + m0 + 127 < p.col0 + n0)) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t bars = sbase + (uint32_t)(STB * BULK_STAGE_ELEMS * sizeof(double));     // full[0..2], empty[0..2]
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(288, 1) dgemm_dmma_bulk_kernel(const GemmParam
     const int KT = p.K / BKB;
     if (warp == 8) {
         // ---- producer warp: lane l moves k-line l of the A tile and of the B tile -----------------------------------
-        const double* Ag = p.A + m0;
-        const double* Bg = TB ? p.B + n0 : p.B + (size_t)n0 * p.ldb;
+        const double* Ag = p.A + (size_t)z * p.sA + m0;
+        const double* Bg = (TB ? p.B + n0 : p.B + (size_t)n0 * p.ldb) + (size_t)z * p.sB;
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % STB;
             mbar_wait(bars + 8 * (STB + s), ((kt / STB) & 1) ^ 1);
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(288, 1) dgemm_dmma_bulk_kernel(const GemmParam
         if (lane == 0) mbar_arrive(bars + 8 * (STB + s));
     }
     const double alpha = p.alpha, beta = p.beta;
+    double* __restrict__ Cz = p.C + (size_t)z * p.sC;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
 #pragma unroll
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(288, 1) dgemm_dmma_bulk_kernel(const GemmParam
             for (int i = 0; i < 8; i++) {
                 const int row = m0 + wm0 + i * 8 + lr;
                 double v = acc[i][j][t];
-                double* cp = p.C + (size_t)col * p.ldc + row;
+                double* cp = Cz + (size_t)col * p.ldc + row;
                 if (p.mode == 1) v = v * v;
                 v *= alpha;
                 if (beta != 0.0) v += beta * (*cp);
@@ -429,12 +431,9 @@ namespace {
 template <int BM, int BN, int BK, int STAGES, int WARPS_M, int WARPS_N, bool TA, bool TB, bool AL>
 void launch_cfg(const GemmParams& p, cudaStream_t st) {
     auto kern = dgemm_dmma_kernel<BM, BN, BK, STAGES, WARPS_M, WARPS_N, TA, TB, AL>;
-    static bool configured = false;
+    static PerDeviceOnce once;               // the shared-memory opt-in is a per-device attribute
     constexpr size_t smem = TileSmem<BM, BN, BK, STAGES>::BYTES;
-    if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    once.run([&] { LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
     dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(p.batch * p.batch2));
     const bool prof = g_prof_on && g_prof.size() < PROF_CAP;
     ProfRec rec;
@@ -492,21 +491,20 @@ void launch_trans(const GemmParams& p, cudaStream_t st) {
 }  // namespace
 
 namespace {
-bool g_bulk_enabled = true;
+std::atomic<bool> g_bulk_enabled{true};
 void launch_bulk(const GemmParams& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    once.run([&] {
         LRN_CUDA(cudaFuncSetAttribute(dgemm_dmma_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BULK_SMEM));
         LRN_CUDA(cudaFuncSetAttribute(dgemm_dmma_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BULK_SMEM));
-        configured = true;
-    }
-    dim3 grid((unsigned)(p.M / 128), (unsigned)(p.N / 128));
+    });
+    dim3 grid((unsigned)(p.M / 128), (unsigned)(p.N / 128), (unsigned)p.batch);
     const bool prof = g_prof_on && g_prof.size() < PROF_CAP;
     ProfRec rec;
     if (prof) {
         LRN_CUDA(cudaEventCreate(&rec.a));
         LRN_CUDA(cudaEventCreate(&rec.b));
-        rec.flops = 2.0 * p.M * (double)p.N * p.K * (p.lower ? 0.5 : 1.0);
+        rec.flops = 2.0 * p.M * (double)p.N * p.K * p.batch * (p.lower ? 0.5 : 1.0);
         LRN_CUDA(cudaEventRecord(rec.a, st));
     }
     if (p.transB) dgemm_dmma_bulk_kernel<true><<<grid, 288, BULK_SMEM, st>>>(p);
@@ -522,15 +520,9 @@ void launch_bulk(const GemmParams& p, cudaStream_t st) {
 }  // namespace
 
 void panel_rotate(const PanelRotateParams& p, cudaStream_t st) {
-    static bool configured = false;
-    static int sms = 148;
-    if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(panel_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_SMEM));
-        int dev = 0;
-        LRN_CUDA(cudaGetDevice(&dev));
-        LRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    once.run([&] { LRN_CUDA(cudaFuncSetAttribute(panel_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_SMEM)); });
+    const int sms = device_sm_count();
     LRN_REQUIRE(p.ldw % 2 == 0 && p.tiles * 128 <= p.ldw, "panel_rotate: rows must be padded to whole 128-row tiles");
     if (p.total <= 0) return;
     const bool prof = g_prof_on && g_prof.size() < PROF_CAP;
@@ -552,41 +544,55 @@ void panel_rotate(const PanelRotateParams& p, cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-void gemm_set_bulk(bool on) { g_bulk_enabled = on; }
+void gemm_set_bulk(bool on) { g_bulk_enabled.store(on); }
+
+int device_sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cached[dev & 63].load(std::memory_order_relaxed);
+    if (v == 0) {
+        LRN_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        cached[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 
 void gemm(const GemmParams& p, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
     // TMA (bulk copy) path: large A B^T and A B products with 16-byte aligned operands.  The kernel takes whole 128 x 128
     // tiles and K in multiples of 32; the bottom / right edge strips and a K remainder (added with beta = 1, plain epilogue
-    // only) go through the generic kernel.
+    // only) go through the generic kernel.  A strided batch (row blocks of the block-cyclic distributed factorisation) is
+    // taken when every problem consists of whole tiles.
     const int Kf = p.K / 32 * 32;
-    if (g_bulk_enabled && !p.ktri && !p.transA && p.batch == 1 && p.batch2 == 1 && !p.colscale && !p.cblkmap && Kf >= 64 &&
-        (Kf == p.K || p.mode == 0) && p.M >= 1024 && p.N >= 1024 && p.row0 == 0 && p.col0 == 0 &&
-        ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && p.lda % 2 == 0 && p.ldb % 2 == 0) {
-        const int Mf = p.M / 128 * 128, Nf = p.N / 128 * 128;
+    const int Mf = p.M / 128 * 128, Nf = p.N / 128 * 128;
+    long long tiles = (long long)(Mf / 128) * (Nf / 128) * p.batch;
+    if (p.lower) tiles = tiles / 2 + Mf / 128;
+    if (g_bulk_enabled.load(std::memory_order_relaxed) && !p.no_bulk && !p.ktri && !p.transA && p.batch2 == 1 && !p.colscale &&
+        !p.cblkmap && Kf >= 64 && (Kf == p.K || p.mode == 0) && Mf >= 128 && Nf >= 128 && tiles >= 120 &&
+        ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.B)) % 16 == 0) && p.lda % 2 == 0 && p.ldb % 2 == 0 &&
+        p.sA % 2 == 0 && p.sB % 2 == 0) {
         GemmParams f = p;
         f.M = Mf; f.N = Nf; f.K = Kf;
         launch_bulk(f, stream);
-        g_bulk_enabled = false;                  // the remainders go through the generic path below
         if (Kf < p.K) {                          // K remainder on the full-tile region
             GemmParams e = f;
             e.A = p.A + (size_t)Kf * p.lda;
             e.B = p.transB ? p.B + (size_t)Kf * p.ldb : p.B + Kf;
-            e.K = p.K - Kf; e.beta = 1.0;
+            e.K = p.K - Kf; e.beta = 1.0; e.no_bulk = true;
             gemm(e, stream);
         }
         if (Mf < p.M) {                          // bottom strip: rows [Mf, M), all columns
             GemmParams e = p;
-            e.A = p.A + Mf; e.C = p.C + Mf; e.M = p.M - Mf; e.row0 = Mf;
+            e.A = p.A + Mf; e.C = p.C + Mf; e.M = p.M - Mf; e.row0 = p.row0 + Mf; e.no_bulk = true;
             gemm(e, stream);
         }
         if (Nf < p.N) {                          // right strip: rows [0, Mf), columns [Nf, N)
             GemmParams e = p;
             e.B = p.transB ? p.B + Nf : p.B + (size_t)Nf * p.ldb;
-            e.C = p.C + (size_t)Nf * p.ldc; e.M = Mf; e.N = p.N - Nf; e.col0 = Nf;
+            e.C = p.C + (size_t)Nf * p.ldc; e.M = Mf; e.N = p.N - Nf; e.col0 = p.col0 + Nf; e.no_bulk = true;
             gemm(e, stream);
         }
-        g_bulk_enabled = true;
         return;
     }
     LRN_REQUIRE(p.A && p.B && p.C, "null operand");

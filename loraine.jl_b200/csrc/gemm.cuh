@@ -30,6 +30,9 @@ struct GemmParams {
     const int* cblkmap = nullptr;
     // global offsets of the sub-problem (only used by the lower-triangle tile test when a product is split into regions)
     int row0 = 0, col0 = 0;
+    long long row0z = 0;      // the outer batch index z1 adds z1 * row0z to row0 (row blocks of a block-cyclic distribution are a
+                              // strided batch: sA = sC = row0z rows further down the same matrix)
+    bool no_bulk = false;     // keep this product off the TMA-fed kernel (edge strips / remainders issued by gemm() itself)
     int ktri = 0;             // 1: op(A) (M x K) and op(B) (K x N) vanish for k < row resp. k < column (product of a transposed
                               // lower-triangular factor with a lower-triangular factor): tiles start their K loop at max(m0, n0)
 };
@@ -58,6 +61,8 @@ inline void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const dou
 long long gemm_launch_count();
 // enable / disable the TMA (cp.async.bulk) fed kernel for large A*B^T products (default on; tests compare both paths)
 void gemm_set_bulk(bool on);
+// number of SMs of the current device (cached per device)
+int device_sm_count();
 
 // Block-Jacobi panel rotation (see panel_rotate_kernel): cur / nxt are column-major work buffers with leading dimension
 // ldw >= 128 * tiles whose padding rows are zero; pair z owns columns [64 z, 64 z + 64) of cur and its rotated halves go

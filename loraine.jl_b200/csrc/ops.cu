@@ -313,13 +313,13 @@ __global__ void __launch_bounds__(256) k_schur_pairs(int npart, int first, const
                                                      const int* __restrict__ rowptr, const int* __restrict__ ep,
                                                      const int* __restrict__ eq, const double* __restrict__ ev,
                                                      const double* __restrict__ W, int ldw, double* __restrict__ H, int ldh,
-                                                     ColOwner own) {
+                                                     RowOwner own) {
     const int kk = first + blockIdx.x * 16 + threadIdx.x;
     const int jj = first + blockIdx.y * 16 + threadIdx.y;
     if (blockIdx.x < blockIdx.y) return;
     if (kk >= npart || jj >= npart || kk < jj) return;
     const int j = part[jj], k = part[kk];
-    if (!own.owns(j < k ? j : k)) return;
+    if (!own.owns(j > k ? j : k)) return;
     const int e0 = rowptr[j], e1 = rowptr[j + 1], f0 = rowptr[k], f1 = rowptr[k + 1];
     double acc = 0.0;
     for (int e = e0; e < e1; e++) {
@@ -335,11 +335,11 @@ __global__ void __launch_bounds__(256) k_schur_pairs(int npart, int first, const
 }
 __global__ void k_schur_f1_column(int npart, int jj, const int* __restrict__ part, const int* __restrict__ rowptr,
                                   const int* __restrict__ ep, const int* __restrict__ eq, const double* __restrict__ ev,
-                                  const double* __restrict__ U, int ldu, double* __restrict__ H, int ldh, ColOwner own) {
+                                  const double* __restrict__ U, int ldu, double* __restrict__ H, int ldh, RowOwner own) {
     int kk = jj + ((blockIdx.x * TB + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (kk >= npart) return;
     const int j = part[jj], k = part[kk];
-    if (!own.owns(j < k ? j : k)) return;
+    if (!own.owns(j > k ? j : k)) return;
     double s = 0.0;
     for (int f = rowptr[k] + lane; f < rowptr[k + 1]; f += 32) s += ev[f] * U[(size_t)eq[f] * ldu + ep[f]];
     s = warp_sum(s);
@@ -375,16 +375,17 @@ __global__ void k_lin_C_x(int n_var, const int* __restrict__ r_ptr, const int* _
 __global__ void k_lin_schur(int n_var, const int* __restrict__ r_ptr, const int* __restrict__ r_col,
                             const double* __restrict__ r_val, const int* __restrict__ c_ptr, const int* __restrict__ c_row,
                             const double* __restrict__ c_val, const double* __restrict__ d, double* __restrict__ H, int ldh,
-                            double* __restrict__ diag, ColOwner own) {
+                            double* __restrict__ diag, RowOwner own) {
     int j = blockIdx.x * TB + threadIdx.x;
     if (j >= n_var) return;
+    if (H && !own.owns(j)) return;          // thread j writes row j of the lower triangle
     for (int t = r_ptr[j]; t < r_ptr[j + 1]; t++) {
         const int r = r_col[t];
         const double w = r_val[t] * d[r];
         if (H) {
             for (int u = c_ptr[r]; u < c_ptr[r + 1]; u++) {
                 const int k = c_row[u];
-                if (k <= j && own.owns(k)) H[(size_t)k * ldh + j] += w * c_val[u];
+                if (k <= j) H[(size_t)k * ldh + j] += w * c_val[u];
             }
         } else {
             diag[j] += w * r_val[t];
@@ -564,7 +565,7 @@ void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int l
     LRN_CHECK_LAUNCH();
 }
 void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh,
-                    ColOwner own) {
+                    RowOwner own) {
     int cnt = sb.npart - first;
     if (cnt <= 0) return;
     unsigned g = (unsigned)cdiv(cnt, 16);
@@ -574,7 +575,7 @@ void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const dou
     LRN_CHECK_LAUNCH();
 }
 void sp_schur_f1_column(cudaStream_t st, const SparseBlock& sb, int jj, const double* U, int ldu, double* H, int ldh,
-                        ColOwner own) {
+                        RowOwner own) {
     int cnt = sb.npart - jj;
     if (cnt <= 0) return;
     k_schur_f1_column<<<(unsigned)cdiv((long long)cnt * 32, TB), TB, 0, st>>>(sb.npart, jj, sb.part.p, sb.rowptr.p, sb.ep.p,
@@ -599,7 +600,7 @@ void lin_C_x(cudaStream_t st, const SparseLin& L, const double* x, double scale,
     k_lin_C_x<<<(unsigned)cdiv(L.n_var, TB), TB, 0, st>>>(L.n_var, L.r_ptr.p, L.r_col.p, L.r_val.p, x, scale, out);
     LRN_CHECK_LAUNCH();
 }
-void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh, ColOwner own) {
+void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh, RowOwner own) {
     if (L.nlin <= 0) return;
     k_lin_schur<<<(unsigned)cdiv(L.n_var, TB), TB, 0, st>>>(L.n_var, L.r_ptr.p, L.r_col.p, L.r_val.p, L.c_ptr.p, L.c_row.p,
                                                             L.c_val.p, d, H, ldh, nullptr, own);
@@ -608,7 +609,7 @@ void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, 
 void lin_schur_diag(cudaStream_t st, const SparseLin& L, const double* d, double* diag) {
     if (L.nlin <= 0) return;
     k_lin_schur<<<(unsigned)cdiv(L.n_var, TB), TB, 0, st>>>(L.n_var, L.r_ptr.p, L.r_col.p, L.r_val.p, L.c_ptr.p, L.c_row.p,
-                                                            L.c_val.p, d, nullptr, 0, diag, ColOwner());
+                                                            L.c_val.p, d, nullptr, 0, diag, RowOwner());
     LRN_CHECK_LAUNCH();
 }
 

@@ -65,14 +65,15 @@ struct Reducer {
     const double* fetch(cudaStream_t st);
 };
 
-// Column ownership of the Schur matrix in multi-GPU runs: 1-D block-cyclic by column panels of width `pw`
-// (panel p -> rank p % world).  world <= 1: everything is owned.
-struct ColOwner {
+// Row ownership of the Schur matrix in multi-GPU runs: 1-D block-cyclic by ROW blocks of height `pw`
+// (row block g -> rank g % world); a rank assembles and factors the part of the lower triangle that lies in its rows
+// (entry (r, c), c <= r, belongs to the owner of row r).  world <= 1: everything is owned.
+struct RowOwner {
     int rank = 0, world = 1, pw = 512;
 #ifdef __CUDACC__
     __host__ __device__
 #endif
-    bool owns(int col) const { return world <= 1 || ((col / pw) % world) == rank; }
+    bool owns(int row) const { return world <= 1 || ((row / pw) % world) == rank; }
 };
 
 // ---- sparse data of one PSD block --------------------------------------------------------------------------------
@@ -131,10 +132,10 @@ void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int l
 // Sparse-pair Schur term (F3 formula, src/makeBBBB.jl:139-213 / _dot :39-64): for participating positions jj <= kk, both >= first,
 //   H[max(j,k), min(j,k)] += tr(calA_j W calA_k W)
 void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh,
-                    ColOwner own = ColOwner());
+                    RowOwner own = RowOwner());
 // F1 column (src/makeBBBB.jl:81-104): given U = W calA_j W dense, H[max(j,k),min(j,k)] += <calA_k, U> for positions kk >= jj
 void sp_schur_f1_column(cudaStream_t st, const SparseBlock& sb, int jj, const double* U, int ldu, double* H, int ldh,
-                        ColOwner own = ColOwner());
+                        RowOwner own = RowOwner());
 // densify calA_j into a zeroed m x m buffer
 void sp_densify(cudaStream_t st, const SparseBlock& sb, int j, double* out, int ld);
 
@@ -152,7 +153,7 @@ void lin_CT_y(cudaStream_t st, const SparseLin& L, const double* y, double scale
 // out[j] += scale * sum_r C[j,r] x[r]
 void lin_C_x(cudaStream_t st, const SparseLin& L, const double* x, double scale, double* out);
 // H[j,k] += sum_r C[j,r] d[r] C[k,r]   for k <= j              (src/predictor_corrector.jl:36-38)
-void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh, ColOwner own = ColOwner());
+void lin_schur(cudaStream_t st, const SparseLin& L, const double* d, double* H, int ldh, RowOwner own = RowOwner());
 // diag[j] += sum_r C[j,r]^2 d[r]
 void lin_schur_diag(cudaStream_t st, const SparseLin& L, const double* d, double* diag);
 

@@ -5,6 +5,7 @@
 //   recurrence      : ConjugateGradients.jl `cg` (un-vendored; call sites src/predictor_corrector.jl:134,235)
 // The whole recurrence keeps its scalars on the device; the host reads one residual norm per iteration.
 #include "solver.cuh"
+#include "group.cuh"
 #include <algorithm>
 #include <cmath>
 
@@ -340,6 +341,7 @@ void ensure_cg(lrn_solver* h) {
 extern "C" {
 
 int32_t lrn_prec_prepare(lrn_handle_t h, int32_t kind) {
+    LRN_GROUP(h, lrn_prec_prepare(m_, kind));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(h->finalized && h->nlmi > 0, "preconditioners need at least one PSD block");
         PhaseT ph(h, LRN_T_PREC);
@@ -355,6 +357,7 @@ int32_t lrn_prec_prepare(lrn_handle_t h, int32_t kind) {
 }
 
 int32_t lrn_pcg(lrn_handle_t h, double tol, int64_t max_iter, int32_t kind, int64_t* num_iters, int32_t* exit_code) {
+    LRN_GROUP(h, lrn_pcg(m_, tol, max_iter, kind, r_ == 0 ? num_iters : group_scratch().i64, r_ == 0 ? exit_code : group_scratch().i32));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(num_iters && exit_code, "null outputs");
         LRN_REQUIRE(kind == 0 || kind == 1 || kind == 2 || kind == 4, "bad preconditioner kind");
@@ -455,6 +458,7 @@ int32_t lrn_pcg(lrn_handle_t h, double tol, int64_t max_iter, int32_t kind, int6
 }
 
 int32_t lrn_apply_operator(lrn_handle_t h, int32_t kind, const double* x, double* out) {
+    if (h && h->group) return lrn_apply_operator(static_cast<Group*>(h->group)->members[0], kind, x, out);
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(x && out, "null pointers");
         ensure_cg(h);

@@ -3,6 +3,7 @@
 // eig.cu / ops.cu and in the small kernels below.
 #include "solver.cuh"
 #include "dist.cuh"
+#include "group.cuh"
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -408,6 +409,7 @@ int32_t lrn_create(lrn_handle_t* out, int64_t n_var, int64_t nlmi, const int64_t
 }
 
 int32_t lrn_set_block_AA(lrn_handle_t h, int64_t i, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    LRN_GROUP(h, lrn_set_block_AA(m_, i, colptr, rowval, nzval));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(i >= 0 && i < h->nlmi && !h->finalized, "bad block index / already finalized");
         copy_csc(h->blk[i].hAA, (int64_t)h->blk[i].m * h->blk[i].m, colptr, rowval, nzval);
@@ -415,6 +417,7 @@ int32_t lrn_set_block_AA(lrn_handle_t h, int64_t i, const int64_t* colptr, const
     });
 }
 int32_t lrn_set_block_C(lrn_handle_t h, int64_t i, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    LRN_GROUP(h, lrn_set_block_C(m_, i, colptr, rowval, nzval));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(i >= 0 && i < h->nlmi && !h->finalized, "bad block index / already finalized");
         copy_csc(h->blk[i].hC, h->blk[i].m, colptr, rowval, nzval);
@@ -422,6 +425,7 @@ int32_t lrn_set_block_C(lrn_handle_t h, int64_t i, const int64_t* colptr, const 
     });
 }
 int32_t lrn_set_block_B(lrn_handle_t h, int64_t i, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    LRN_GROUP(h, lrn_set_block_B(m_, i, colptr, rowval, nzval));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(i >= 0 && i < h->nlmi && !h->finalized, "bad block index / already finalized");
         copy_csc(h->blk[i].hB, h->blk[i].m, colptr, rowval, nzval);
@@ -429,6 +433,7 @@ int32_t lrn_set_block_B(lrn_handle_t h, int64_t i, const int64_t* colptr, const 
     });
 }
 int32_t lrn_set_lin(lrn_handle_t h, const int64_t* colptr, const int64_t* rowval, const double* nzval, const double* d_lin) {
+    LRN_GROUP(h, lrn_set_lin(m_, colptr, rowval, nzval, d_lin));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(!h->finalized, "already finalized");
         if (h->nlin == 0) return LRN_OK;
@@ -443,6 +448,7 @@ int32_t lrn_set_lin(lrn_handle_t h, const int64_t* colptr, const int64_t* rowval
     });
 }
 int32_t lrn_set_b(lrn_handle_t h, const double* b) {
+    LRN_GROUP(h, lrn_set_b(m_, b));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(b, "b is null");
         h->b.upload(b, h->n_var, h->st);
@@ -455,6 +461,7 @@ int32_t lrn_set_b(lrn_handle_t h, const double* b) {
 }
 
 int32_t lrn_finalize(lrn_handle_t h) {
+    LRN_GROUP(h, lrn_finalize(m_));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(!h->finalized, "already finalized");
         LRN_REQUIRE(h->b.p, "lrn_set_b was not called");
@@ -552,6 +559,16 @@ int32_t lrn_finalize(lrn_handle_t h) {
 
 int32_t lrn_destroy(lrn_handle_t h) {
     if (!h) return LRN_OK;
+    if (h->group) {
+        Group* g = static_cast<Group*>(h->group);
+        // the communicators of one ncclCommInitAll clique are destroyed from concurrent threads (ncclCommDestroy may wait for peers)
+        std::vector<std::thread> th;
+        for (auto* m : g->members) th.emplace_back([m] { lrn_destroy(m); });
+        for (auto& t : th) t.join();
+        delete g;
+        delete h;
+        return LRN_OK;
+    }
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -560,16 +577,23 @@ int32_t lrn_destroy(lrn_handle_t h) {
     for (auto& s_ : h->side) if (s_) { cudaStreamSynchronize(s_); cudaStreamDestroy(s_); }
     if (h->evFork) cudaEventDestroy(h->evFork);
     for (auto& e : h->evJoin) if (e) cudaEventDestroy(e);
+    if (h->nccl) { delete static_cast<DistCtx*>(h->nccl); h->nccl = nullptr; }
     delete h;
     if (st) cudaStreamDestroy(st);
     return LRN_OK;
 }
 
-const char* lrn_last_error(lrn_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+const char* lrn_last_error(lrn_handle_t h) {
+    if (!h) return "null handle";
+    if (h->group && h->err.empty() && !static_cast<Group*>(h->group)->members.empty())
+        return static_cast<Group*>(h->group)->members[0]->err.c_str();
+    return h->err.c_str();
+}
 
 // ---- iterate ----------------------------------------------------------------------------------------------------------
 int32_t lrn_set_iterate(lrn_handle_t h, const double* const* X, const double* const* S, const double* y, const double* x_lin,
                         const double* s_lin) {
+    LRN_GROUP(h, lrn_set_iterate(m_, X, S, y, x_lin, s_lin));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(h->finalized, "lrn_finalize first");
         for (int i = 0; i < h->nlmi; i++) {
@@ -594,6 +618,7 @@ int32_t lrn_set_iterate(lrn_handle_t h, const double* const* X, const double* co
 }
 
 int32_t lrn_get_solution(lrn_handle_t h, double* y, double* const* X, double* x_lin) {
+    if (h && h->group) return lrn_get_solution(static_cast<Group*>(h->group)->members[0], y, X, x_lin);
     return guarded(h, [&]() -> int32_t {
         if (y) LRN_CUDA(cudaMemcpyAsync(y, h->y.p, h->n_var * sizeof(double), cudaMemcpyDeviceToHost, h->st));
         if (X)
@@ -607,6 +632,7 @@ int32_t lrn_get_solution(lrn_handle_t h, double* y, double* const* X, double* x_
 }
 
 int32_t lrn_get_slack(lrn_handle_t h, double* const* S, double* s_lin) {
+    if (h && h->group) return lrn_get_slack(static_cast<Group*>(h->group)->members[0], S, s_lin);
     return guarded(h, [&]() -> int32_t {
         if (S)
             for (int i = 0; i < h->nlmi; i++)
@@ -662,6 +688,7 @@ static void side_join(lrn_solver* h) {
 
 // ---- hot path -------------------------------------------------------------------------------------------------------
 int32_t lrn_find_mu(lrn_handle_t h, double* mu) {
+    LRN_GROUP(h, lrn_find_mu(m_, r_ == 0 ? mu : group_scratch().d));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(mu, "null output");
         cudaStream_t st = h->st;
@@ -675,6 +702,7 @@ int32_t lrn_find_mu(lrn_handle_t h, double* mu) {
 }
 
 int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
+    LRN_GROUP(h, lrn_prepare_W(m_, r_ == 0 ? status4 : group_scratch().i32));
     return guarded(h, [&]() -> int32_t {
         Phase ph(h, LRN_T_PREPARE_W);
         cudaStream_t st = h->st;
@@ -742,6 +770,7 @@ int32_t lrn_prepare_W(lrn_handle_t h, int32_t* status4) {
 }
 
 int32_t lrn_residuals(lrn_handle_t h) {
+    LRN_GROUP(h, lrn_residuals(m_));
     return guarded(h, [&]() -> int32_t {
         Phase ph(h, LRN_T_RESIDUALS);
         cudaStream_t st = h->st;
@@ -763,6 +792,7 @@ int32_t lrn_residuals(lrn_handle_t h) {
 }
 
 int32_t lrn_schur_assemble(lrn_handle_t h) {
+    LRN_GROUP(h, lrn_schur_assemble(m_));
     return guarded(h, [&]() -> int32_t {
         for (auto& Bk : h->blk) Bk.ud_valid = false;
         LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
@@ -770,7 +800,8 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
         cudaStream_t st = h->st;
         const int n = h->n_var;
         LRN_CUDA(cudaMemsetAsync(h->H.p(), 0, h->H.bytes(), st));
-        ColOwner own;                                  // multi-GPU: every rank assembles only the column panels it owns
+        h->H_gathered = false;
+        RowOwner own;                                  // multi-GPU: every rank assembles only the row blocks it owns
         own.rank = h->rank; own.world = h->world; own.pw = h->dist_pw;
         for (auto& B : h->blk) {
             const int m = B.m, ld = B.ld;
@@ -784,18 +815,8 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
                 p.A = h->BG.p(); p.B = h->BG.p(); p.C = h->H.p();
                 p.M = n; p.N = n; p.K = Kp; p.lda = h->BG.ld; p.ldb = h->BG.ld; p.ldc = h->H.ld;
                 p.transB = true; p.alpha = 1.0; p.beta = 1.0; p.mode = 1; p.lower = 1;
-                if (h->world <= 1) {
-                    gemm(p, st);
-                } else {
-                    for (int q0 = 0; q0 < n; q0 += own.pw) {
-                        if (!own.owns(q0)) continue;
-                        GemmParams q = p;
-                        q.lower = 0;
-                        q.A = h->BG.p() + q0; q.B = h->BG.p() + q0; q.C = h->H.p() + (size_t)q0 * h->H.ld + q0;
-                        q.M = n - q0; q.N = std::min(own.pw, n - q0);
-                        gemm(q, st);
-                    }
-                }
+                if (h->world <= 1) gemm(p, st);
+                else syrk_sq_row_blocks(h->BG.p(), h->BG.ld, n, Kp, h->H.p(), h->H.ld, own.rank, own.world, own.pw, st);
             } else {
                 for (int jj = 0; jj < B.sp.nF1; jj++) {
                     // F1: U = W calA_j W, column of <calA_k, U>                (src/makeBBBB.jl:81-104)
@@ -827,6 +848,7 @@ static void add_lp_rhs(lrn_solver* h, int corr, double sigmamu) {
 }
 
 int32_t lrn_rhs_predictor(lrn_handle_t h) {
+    LRN_GROUP(h, lrn_rhs_predictor(m_));
     return guarded(h, [&]() -> int32_t {
         for (auto& Bk : h->blk) Bk.ud_valid = false;
         Phase ph(h, LRN_T_RHS);
@@ -853,6 +875,7 @@ int32_t lrn_rhs_predictor(lrn_handle_t h) {
 }
 
 int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
+    LRN_GROUP(h, lrn_rhs_corrector(m_, sigma, mu));
     return guarded(h, [&]() -> int32_t {
         for (auto& Bk : h->blk) Bk.ud_valid = false;
         Phase ph(h, LRN_T_RHS);
@@ -888,6 +911,7 @@ int32_t lrn_rhs_corrector(lrn_handle_t h, double sigma, double mu) {
 }
 
 int32_t lrn_schur_factor(lrn_handle_t h) {
+    LRN_GROUP(h, lrn_schur_factor(m_));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
         int info = 0;
@@ -896,7 +920,7 @@ int32_t lrn_schur_factor(lrn_handle_t h) {
             cudaStream_t st = h->st;
             LRN_CUDA(cudaMemcpyAsync(h->L.p(), h->H.p(), h->H.bytes(), cudaMemcpyDeviceToDevice, st));
             if (h->world > 1)
-                cholesky_dist(h->L.p(), h->n_var, h->L.ld, h->cholH, *static_cast<DistCtx*>(h->nccl), h->dist_pw, h->panelbuf, st);
+                cholesky_dist(h->L.p(), h->n_var, h->L.ld, h->cholH, *static_cast<DistCtx*>(h->nccl), h->dist_pw, st);
             else
                 cholesky_lower(h->L.p(), h->n_var, h->L.ld, h->cholH, st);
             LRN_CUDA(cudaMemcpyAsync(&info, h->cholH.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -908,15 +932,26 @@ int32_t lrn_schur_factor(lrn_handle_t h) {
 }
 
 int32_t lrn_schur_shift(lrn_handle_t h, double delta) {
+    LRN_GROUP(h, lrn_schur_shift(m_, delta));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
-        mat_add_diag(h->st, h->n_var, h->H.p(), h->H.ld, delta);
+        if (h->world > 1 && !h->H_gathered) {
+            // sharded rows: every rank shifts the diagonal entries of its own row blocks only
+            const int pw = h->dist_pw, n = h->n_var;
+            for (int g = h->rank; g * pw < n; g += h->world) {
+                const int r0 = g * pw, rb = std::min(pw, n - r0);
+                mat_add_diag(h->st, rb, h->H.p() + (size_t)r0 * h->H.ld + r0, h->H.ld, delta);
+            }
+        } else {
+            mat_add_diag(h->st, h->n_var, h->H.p(), h->H.ld, delta);
+        }
         h->have_factor = false;
         return LRN_OK;
     });
 }
 
 int32_t lrn_schur_solve(lrn_handle_t h, int32_t which) {
+    LRN_GROUP(h, lrn_schur_solve(m_, which));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(h->have_factor, "no valid Cholesky factor (call lrn_schur_factor)");
         LRN_REQUIRE(which == 1 || which == 2 || which == 3 || which == 6, "which must be 1, 2, 3 or 6");
@@ -932,6 +967,14 @@ int32_t lrn_schur_solve(lrn_handle_t h, int32_t which) {
 
 int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, double tau, double* alpha, double* beta,
                       double* alpha_lin, double* beta_lin) {
+    if (h && h->group)
+        return group_call(h, [&](lrn_solver* m_, int r_) -> int32_t {
+            if (r_ == 0) return lrn_find_step(m_, predict, sigma, mu, tau, alpha, beta, alpha_lin, beta_lin);
+            GroupScratch& g = group_scratch();
+            g.a.assign(std::max(1, m_->nlmi), 0.0);
+            g.b.assign(std::max(1, m_->nlmi), 0.0);
+            return lrn_find_step(m_, predict, sigma, mu, tau, g.a.data(), g.b.data(), g.d, g.d + 1);
+        });
     return guarded(h, [&]() -> int32_t {
         for (auto& Bk : h->blk) Bk.ud_valid = false;
         LRN_REQUIRE((h->nlmi == 0 || (alpha && beta)) && alpha_lin && beta_lin, "null outputs");
@@ -1063,6 +1106,7 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
 }
 
 int32_t lrn_sigma_trace(lrn_handle_t h, double* tr, double* dl) {
+    LRN_GROUP(h, lrn_sigma_trace(m_, r_ == 0 ? tr : group_scratch().d, r_ == 0 ? dl : group_scratch().d + 1));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(tr && dl, "null outputs");
         cudaStream_t st = h->st;
@@ -1077,6 +1121,8 @@ int32_t lrn_sigma_trace(lrn_handle_t h, double* tr, double* dl) {
 }
 
 int32_t lrn_dimacs(lrn_handle_t h, double* err6, double* by_out, double* trCX_out, double* dx_out) {
+    LRN_GROUP(h, r_ == 0 ? lrn_dimacs(m_, err6, by_out, trCX_out, dx_out)
+                       : lrn_dimacs(m_, group_scratch().d, nullptr, nullptr, nullptr));
     return guarded(h, [&]() -> int32_t {
         for (auto& Bk : h->blk) Bk.ud_valid = false;
         LRN_REQUIRE(err6, "null output");
@@ -1170,8 +1216,11 @@ int32_t lrn_dimacs(lrn_handle_t h, double* err6, double* by_out, double* trCX_ou
 
 // ---- parity hooks -------------------------------------------------------------------------------------------------------
 int32_t lrn_get_array(lrn_handle_t h, int32_t which, int64_t iblk, double* out) {
+    // Schur matrix: a collective (every member contributes its row blocks); everything else is replicated -> member 0
+    if (h && h->group && which != LRN_ARR_H) return lrn_get_array(static_cast<Group*>(h->group)->members[0], which, iblk, out);
+    LRN_GROUP(h, lrn_get_array(m_, which, iblk, r_ == 0 ? out : nullptr));
     return guarded(h, [&]() -> int32_t {
-        LRN_REQUIRE(out, "null output");
+        LRN_REQUIRE(out || which == LRN_ARR_H, "null output");
         cudaStream_t st = h->st;
         const int n = h->n_var;
         auto vec_out = [&](const double* p, int len) {
@@ -1181,11 +1230,14 @@ int32_t lrn_get_array(lrn_handle_t h, int32_t which, int64_t iblk, double* out) 
             LRN_REQUIRE(h->H.p(), "Schur matrix is only allocated for kit = 0");
             DMat& M = (which == LRN_ARR_H) ? h->H : h->L;
             // work on a copy in tn-sized chunks is not possible: use the spare matrix of the other kind only when safe
-            if (which == LRN_ARR_H && h->world > 1)      // every rank holds only its own column panels: sum them up
+            if (which == LRN_ARR_H && h->world > 1 && h->nccl && static_cast<DistCtx*>(h->nccl)->comm && !h->H_gathered) {
+                // every rank holds only its own row blocks: sum them up (once per assembly)
                 dist_allreduce_sum(M.p(), (size_t)M.ld * n, *static_cast<DistCtx*>(h->nccl), st);
+                h->H_gathered = true;
+            }
             if (which == LRN_ARR_H) mat_mirror_lower(st, n, M.p(), M.ld);
             else zero_strict_upper(M.p(), n, M.ld, st);
-            download_dense(h, M.p(), M.ld, n, n, out);
+            if (out) download_dense(h, M.p(), M.ld, n, n, out);
         } else if (which == LRN_ARR_RHS) vec_out(h->rhs.p, n);
         else if (which == LRN_ARR_DELY) vec_out(h->dely.p, n);
         else if (which == LRN_ARR_RP) vec_out(h->Rp.p, n);
@@ -1226,6 +1278,7 @@ int32_t lrn_get_array(lrn_handle_t h, int32_t which, int64_t iblk, double* out) 
 }
 
 int32_t lrn_timers(lrn_handle_t h, double* ms, int64_t* calls, int32_t reset) {
+    if (h && h->group) return lrn_timers(static_cast<Group*>(h->group)->members[0], ms, calls, reset);
     return guarded(h, [&]() -> int32_t {
         flush_timers(h);
         for (int i = 0; i < LRN_T_COUNT; i++) {
@@ -1238,6 +1291,7 @@ int32_t lrn_timers(lrn_handle_t h, double* ms, int64_t* calls, int32_t reset) {
 }
 
 int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
+    LRN_GROUP(h, lrn_set_option(m_, name, value));
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(name, "null name");
         std::string n(name);
@@ -1261,6 +1315,7 @@ int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
 int64_t lrn_kernel_launches(void) { return (int64_t)lrn::g_kernel_launches.load(); }
 
 int32_t lrn_stats(lrn_handle_t h, int64_t* out3) {
+    if (h && h->group) return lrn_stats(static_cast<Group*>(h->group)->members[0], out3);
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(out3, "null output");
         out3[0] = h->stat_svd_sweeps; out3[1] = h->stat_lanczos_iters; out3[2] = h->stat_lanczos_fail;
