@@ -1,14 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the Loraine.jl per-iteration interior-point hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C3|C4|C5|...-mini]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C5|C2|C3|C4|...-mini]
 
-A "step" is ONE interior-point iteration (find_mu, prepare_W, predictor, sigma_update, corrector, check_convergence) of
-the workload BASELINE.json's metric is quoted on: configs[1], the synthetic Max-Cut SDP n = 5000 with the rank-one Schur
-path (datarank = -1, kit = 0).  `value` = seconds per IP iteration with the problem and the iterate resident in HBM;
-`e2e` = the same iteration driven through the C ABI with the iterate in HOST memory (upload X, S, y / download y, X, S
-inside the timed region).  Multi-GPU (--gpus N under torchrun): this workload has a single PSD block, the path does not
-shard ("replicas only"): every rank runs an independent replica and `value` is job seconds per iteration.
+A "step" is ONE interior-point iteration (find_mu, prepare_W, predictor, sigma_update, corrector, check_convergence).
+The workload is the configuration BASELINE.json's metric ("... at 1/2/4/8 B200") is quoted on: configs[4], the synthetic
+large-Schur SDP with n_var = 40000 constraints and one PSD block of side 1000 (kit = 0).  It fits one GPU, so it is the
+workload for EVERY N, 1 included: `--gpus N` (under torchrun) runs ONE solve whose Schur assembly and Cholesky
+factorisation are sharded over the N ranks (row-block-cyclic, NCCL) -- strong scaling; `value` = seconds per iteration of
+that one solve, max over ranks.  At N = 1 the line also carries the single-GPU configs[1..3] as `sub_records`.
+
+`value`  : seconds per IP iteration with the problem and the iterate resident in HBM.
+`e2e`    : the same iteration driven through the C ABI with the iterate in HOST (pinned) memory: X, S, y uploaded before and
+           downloaded after every iteration inside the timed region.
+`cpu_baseline` / `--impl reference`: the reference's CPU algorithm on the SAME full-size instance on the box's host cores.
+           Julia is not in the image, so this is the NumPy/LAPACK oracle ("port"; sparse Schur assembly through the plain-C
+           restatement oracle/schur_pairs.c, dpotrf in place).  One CPU iteration of configs[4] takes tens of seconds, so
+           the arm measures at most 1 warm-up + 2 timed iterations and says so (`steps`, `steps_requested`).
 """
 from __future__ import annotations
 
@@ -36,10 +44,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2")
-    ap.add_argument("--cpu-sample-n", type=int, default=2000, help="side of the reduced instance timed on the host CPU")
+    ap.add_argument("--workload", default="C5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the end-to-end solve to convergence reported under `solve`")
+    ap.add_argument("--no-sub", action="store_true", help="N = 1: skip the configs[1..3] sub-records")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-single-GPU parity check")
+    ap.add_argument("--cpu-max-steps", type=int, default=2, help="reference arm: timed CPU iterations are capped at this number")
     return ap.parse_args()
 
 
@@ -117,62 +127,6 @@ def use_all_host_threads():
         return int(os.environ.get("OMP_NUM_THREADS", n))
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """The reference's CPU implementation of the path on the host cores.  Julia is not installed in this image, so the
-    arm executes the NumPy/LAPACK oracle (oracle/loraine_oracle.py, kind = "port") with all host threads."""
-    rank, world, local = dist_env()
-    if rank != 0:
-        return
-    import __graft_entry__ as g
-    pkg = g.load_package()
-    from oracle import loraine_oracle as lo, sdpa_io
-    blas_threads = use_all_host_threads()
-    cfg = pkg.problems.CONFIGS[args.workload]
-    full = cfg["gen"]
-    ns = args.cpu_sample_n
-    sample_note = ""
-    scale = 1.0
-    if args.workload == "C2":
-        rows = 25
-        cols = max(4, ns // rows)
-        arrays = pkg.problems.maxcut_torus(rows, cols, 5000)
-        nfull = 5000
-        scale = (nfull / float(rows * cols)) ** 3
-        sample_note = (f"max-cut torus {rows}x{cols} (n = m = {rows * cols}) from the same generator/seed; every phase of the "
-                       f"iteration is O(n^3) dense work, seconds scaled by (5000/{rows * cols})^3 = {scale:.1f} to the full size "
-                       f"(explicit extrapolation; the full-size CPU iteration takes minutes)")
-    else:
-        arrays = full()
-        sample_note = "full-size instance"
-    o = dict(cfg["options"], verb=0)
-    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=int(o.get("datarank", 0)), kappa=int(o.get("datasparsity", 8)))
-    s, ha = lo.load(md, o)
-    lo.setup_solver(s, ha)
-    lo.initial_point(s)
-
-    def step():
-        lo.myIPstep(s, ha)
-        s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
-        lo.check_convergence(s)
-        if s.status != 0:
-            lo.initial_point(s)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    raw = (time.perf_counter() - t0) / args.steps
-    cores = blas_threads
-    val = raw * scale
-    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=val * 1e3,
-                higher_is_better=False, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=workload_name(args.workload), sample=sample_note),
-                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample_note, measured_s_per_iteration_on_sample=raw),
-                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
-
-
 def workload_name(w):
     return {"C5": "configs[4]: synthetic large-Schur SDP n_var=40000 constraints, 1 PSD block m=1000, kit=0, datarank=0 (seed 40000)",
             "C4": "configs[3]: synthetic multi-block SDP, 50 PSD blocks of size 200 + LP block of 2000 rows, n_var=10000, kit=0",
@@ -182,57 +136,115 @@ def workload_name(w):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def run_b200(args):
-    rank, world, local = dist_env()
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # keep stdout for the one JSON line: NCCL's own messages (version banner, INFO) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import __graft_entry__ as g
-    pkg = g.load_package()
-    from loraine_jl_b200 import solver as S, _lib
-    L = _lib.lib()
-    L.lrn_dbg_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
-    L.lrn_dbg_gemm_profile.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-
-    cfg = pkg.problems.CONFIGS[args.workload]
+#  CPU arm: the oracle ("port") on the SAME full-size instance
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_iterations(pkg, workload, warmup, steps):
+    """runs warmup + steps interior-point iterations of the oracle on the full-size instance of `workload` with all host
+    threads; returns (seconds per timed iteration, description, threads, per-phase seconds of the timed iterations)"""
+    from oracle import loraine_oracle as lo, sdpa_io, c_oracle
+    blas_threads = use_all_host_threads()
+    cfg = pkg.problems.CONFIGS[workload]
     arrays = cfg["gen"]()
-    opt = pkg.Optimizer()
-    for k, v in dict(cfg["options"], verb=0, device=local).items():
-        opt.set_attribute(k, v)
-    opt.copy_to(pkg.raw_from_sdpa_arrays(*arrays))
-    s, ha = opt.solver, opt.halpha
-    S.setup_solver(s, ha)
-    sharded = False
-    if world > 1 and args.workload.startswith("C5"):
-        sharded = pkg.dist.init_distributed(s)      # Schur assembly + Cholesky sharded over the ranks (NCCL panel broadcast)
-    S.initial_point(s)
-    md = s.model
+    o = dict(cfg["options"], verb=0)
+    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=int(o.get("datarank", 0)), kappa=int(o.get("datasparsity", 8)))
+    s, ha = lo.load(md, o)
+    # large general-path instances: sparse Schur assembly through oracle/schur_pairs.c (the NumPy form needs minutes at
+    # n_var = 40000), Cholesky in place; same arithmetic (pinned in tests/test_oracle_golden.py)
+    s.lean = bool(md.n >= 4000 and int(o.get("datarank", 0)) != -1 and int(o.get("kit", 0)) == 0)
+    threads = blas_threads
+    if s.lean:
+        threads = max(threads, c_oracle.max_threads())
+    lo.setup_solver(s, ha)
+    lo.initial_point(s)
 
     def step():
-        S.myIPstep(s, ha)
+        lo.myIPstep(s, ha)
+        s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
+        lo.check_convergence(s)
+        if s.status != 0:
+            lo.initial_point(s)
+    for _ in range(warmup):
+        step()
+    s.phase_time = {}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    raw = (time.perf_counter() - t0) / max(1, steps)
+    note = (f"full-size instance (same generator, seed and options as the GPU arm), {warmup} warm-up + {steps} timed IP iteration(s) of "
+            f"the NumPy/LAPACK oracle" + (" with the plain-C sparse Schur assembly (oracle/schur_pairs.c) and in-place dpotrf" if s.lean else ""))
+    return raw, note, threads, {k: v / max(1, steps) for k, v in s.phase_time.items()}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores.  Julia is not installed in this image, so the
+    arm executes the NumPy/LAPACK oracle (oracle/, kind = "port") with all host threads on the full-size instance."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, args.cpu_max_steps))
+    raw, note, cores, phases = cpu_iterations(pkg, args.workload, warm, steps)
+    line = dict(metric=METRIC, value=raw, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm, steps_requested=args.steps,
+                warmup_requested=args.warmup, ms_per_step=raw * 1e3, higher_is_better=False, scaling="strong", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=workload_name(args.workload), sample=note, same_config=True),
+                cpu_baseline=dict(value=raw, unit=UNIT, cores=cores, kind="port", sample=note, phases_s_per_iteration=phases),
+                e2e=dict(value=raw, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+#  GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class Runner:
+    """one workload on this rank's GPU (sharded over the job's ranks when the workload is configs[4] and world > 1)"""
+
+    def __init__(self, pkg, workload, local, sharded):
+        from loraine_jl_b200 import solver as S
+        self.S, self.pkg, self.workload, self.local = S, pkg, workload, local
+        self.cfg = pkg.problems.CONFIGS[workload]
+        self.arrays = self.cfg["gen"]()
+        self.opt = self._optimizer()
+        self.s, self.ha = self.opt.solver, self.opt.halpha
+        S.setup_solver(self.s, self.ha)
+        self.sharded = bool(sharded and pkg.dist.init_distributed(self.s))
+        S.initial_point(self.s)
+
+    def _optimizer(self):
+        opt = self.pkg.Optimizer()
+        for k, v in dict(self.cfg["options"], verb=0, device=self.local).items():
+            opt.set_attribute(k, v)
+        opt.copy_to(self.pkg.raw_from_sdpa_arrays(*self.arrays))
+        return opt
+
+    def make_single(self):
+        """a second, single-GPU solver of the same instance on the same device (parity reference of the sharded path)"""
+        opt = self._optimizer()
+        self.S.setup_solver(opt.solver, opt.halpha)
+        return opt.solver
+
+    def step(self, sync_status=None):
+        S, s = self.S, self.s
+        S.myIPstep(s, self.ha)
         s.itertime = 0.0
         s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
         S.check_convergence(s)
-        if s.status != 0:               # converged (or failed): restart the same solve so that every step is a real iteration
+        st = s.status if sync_status is None else sync_status(s.status)
+        if st != 0:               # converged (or failed): restart the same solve so that every step is a real iteration
             S.initial_point(s)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
+def measure(run, args, world, rank, barrier, sync_status, L, want_solve):
+    """timed device-resident steps, e2e steps, per-launch DMMA profile, optional full solve -> dict of raw results"""
+    import torch
+    S, s, md = run.S, run.s, run.s.model
+    warm = max(args.warmup, 3)
     tol_cg0 = s.tol_cg
-    for _ in range(max(args.warmup, 3)):
-        step()
-    # ---- timed region: device-resident iterations -------------------------------------------------------------------
-    sampler = ClockSampler(local)
+    for _ in range(warm):
+        run.step(sync_status)
+    sampler = ClockSampler(run.local)
     if rank == 0:
         sampler.start()
     s.timers(reset=True)
@@ -240,14 +252,13 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        run.step(sync_status)
     barrier()
     t_dev = time.perf_counter() - t0
     launches = L.lrn_kernel_launches() - launches0
     phase = s.timers(reset=True)
     clocks = sampler.stop() if rank == 0 else None
     # ---- e2e: the iterate lives in HOST memory; upload before / download after every iteration ------------------------
-    # same iterations as the device-timed region: restart from the initial point, run the same warm-up, time the same K steps
     S.initial_point(s)
     s.tol_cg = tol_cg0
     y, X, xl = S.get_solution(s)
@@ -262,151 +273,194 @@ def run_b200(args):
     yh, xlh, slh = pin(y), pin(xl), pin(sl)
     Shp = (PD * max(1, md.nlmi))(*[x.ctypes.data_as(PD) for x in Sh])
     h2d = sum(x.nbytes for x in Xh) + sum(x.nbytes for x in Sh) + yh.nbytes + xlh.nbytes + slh.nbytes
-    d2h = h2d
-    e2e_steps = args.steps
 
     def e2e_step():
         S.set_iterate(s, Xh, Sh, yh, xlh, slh)                      # H2D from the pinned buffers
-        S.myIPstep(s, ha)
+        S.myIPstep(s, run.ha)
         s.itertime = 0.0
         s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
         S.check_convergence(s)
-        if s.status != 0:
+        st = s.status if sync_status is None else sync_status(s.status)
+        if st != 0:
             S.initial_point(s)
         S.get_solution(s, out=(yh, Xh, xlh))                        # D2H straight into the pinned buffers
         s._call("lrn_get_slack", Shp, slh.ctypes.data_as(PD) if md.nlin else None)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         e2e_step()
     barrier()
     t_e2e = time.perf_counter() - t0
-    # ---- roofline pass: per-launch CUDA events around the dominant kernel (the DMMA GEMM) ---------------------------
+    # ---- roofline pass: per-launch CUDA events around every DMMA GEMM launch (on the launching stream) ----------------
     ms, fl, nl = C.c_double(), C.c_double(), C.c_int64()
     L.lrn_dbg_gemm_profile(1, None, None, None)
-    prof_steps = 1
-    for _ in range(prof_steps):
-        step()
+    run.step(sync_status)
     L.lrn_dbg_gemm_profile(0, C.byref(ms), C.byref(fl), C.byref(nl))
-    peak = C.c_double()
-    L.lrn_dbg_peak(0, C.byref(peak))
-    # ---- end-to-end solve to the reference's stopping rule (outside the timed regions; every rank runs it) ---------------
+    fams = []
+    for code, kname in ((10, "dgemm_dmma_kernel (cp.async-fed DMMA GEMM: congruences, Gram products, TRSM, edge strips)"),
+                        (11, "dgemm_dmma_bulk_kernel (TMA-fed DMMA GEMM: Schur SYRK, Cholesky trailing updates, panel solves, large congruences)"),
+                        (12, "panel_rotate_kernel (TMA-fed DMMA panel rotation of the block-Jacobi SVD)")):
+        fm, ff, fn = C.c_double(), C.c_double(), C.c_int64()
+        L.lrn_dbg_gemm_profile(code, C.byref(fm), C.byref(ff), C.byref(fn))
+        if fn.value > 0 and fm.value > 0:
+            fams.append(dict(kernel=kname, launches=int(fn.value), kernel_ms_per_step=fm.value,
+                             algorithmic_flops_per_launch=ff.value / fn.value,
+                             avg_launch_us=1e3 * fm.value / fn.value, achieved=ff.value / (fm.value * 1e-3) / 1e12))
+    # ---- end-to-end solve to the reference's stopping rule (outside the timed regions) -------------------------------
     solve_info = None
-    if not args.no_solve:
+    if want_solve:
         barrier()
         t0 = time.perf_counter()
-        S.solve(s, ha)
+        if sync_status is None:
+            S.solve(s, run.ha, setup=False)
+        else:                                   # sharded: same loop, the termination test is agreed between the ranks
+            S.initial_point(s)
+            while True:
+                S.myIPstep(s, run.ha)
+                s.tol_cg = max(s.tol_cg * s.tol_cg_up, s.tol_cg_min)
+                S.check_convergence(s)
+                if sync_status(s.status) != 0 or s.iter > s.maxit:
+                    break
         barrier()
         solve_info = dict(seconds=time.perf_counter() - t0, iterations=int(s.iter), status=int(s.status),
                           dimacs_error=float(s.DIMACS_error), primal_obj=float(s.primal_obj), dual_obj=float(s.dual_obj),
                           cg_iterations=int(s.cg_iter_tot) if s.kit == 1 else None)
+    alg = algorithmic_flops(md, int(s.datarank))
+    asm_ms = phase["schur_assemble"][0] / max(1, phase["schur_assemble"][1])
+    fac_ms = phase["schur_factor"][0] / max(1, phase["schur_factor"][1])
+    schur = dict(assemble_ms=asm_ms, assemble_tflops=alg["assemble"] / (asm_ms * 1e-3) / 1e12 if asm_ms > 0 else None,
+                 factor_ms=fac_ms, factor_tflops=alg["factor"] / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else None,
+                 assemble_plus_factor_tflops=(alg["assemble"] + alg["factor"]) / ((asm_ms + fac_ms) * 1e-3) / 1e12
+                 if asm_ms + fac_ms > 0 else None,
+                 note="algorithmic flops of the WHOLE matrix (SURVEY 8(d)) over this rank's phase time: aggregate rate of the job")
+    return dict(t_dev=t_dev, t_e2e=t_e2e, launches=int(launches), phase=phase, clocks=clocks, h2d=int(h2d), fams=fams,
+                all_dmma=dict(ms=ms.value, flops=fl.value, launches=int(nl.value)), solve=solve_info, schur=schur,
+                stats=s.stats(), warm=warm)
 
-    tmax = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+
+def run_b200(args):
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        # keep stdout for the one JSON line: NCCL's own messages (version banner, INFO) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from loraine_jl_b200 import _lib
+    L = _lib.lib()
+    L.lrn_dbg_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    L.lrn_dbg_gemm_profile.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    shardable = args.workload.startswith("C5") or args.workload.startswith("C2")
+    run = Runner(pkg, args.workload, local, sharded=(world > 1 and shardable))
+    sync_status = None
+    if world > 1 and run.sharded:
+        flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+
+        def sync_status(st):                     # every rank takes the same restart / stop decision (collectives must line up)
+            flag[0] = int(st)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            return int(flag.item())
+    s, md = run.s, run.s.model
+    res = measure(run, args, world, rank, barrier, sync_status, L, want_solve=not args.no_solve)
+    # ---- sharded path against the single-GPU path on the same inputs (outside the timed regions) ---------------------
+    parity = None
+    if run.sharded and not args.no_parity:
+        parity = pkg.dist.dist_parity(s, run.make_single, rank, iters=2)
+    tmax = torch.tensor([res["t_dev"], res["t_e2e"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(tmax[0]), float(tmax[1])
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
-    # replicas: the job advances `world` independent solves per step; sharded: all ranks advance ONE solve together
-    units = 1 if sharded else world
+    peak = C.c_double()
+    L.lrn_dbg_peak(0, C.byref(peak))
+    # sharded: all ranks advance ONE solve together; replicas (a workload that does not shard): `world` independent solves
+    units = 1 if (run.sharded or world == 1) else world
     sec_per_iter = t_dev / (args.steps * units)
-    e2e_val = t_e2e / (e2e_steps * units)
-    alg = algorithmic_flops(md, int(s.datarank))
-    asm_ms = phase["schur_assemble"][0] / max(1, phase["schur_assemble"][1])
-    fac_ms = phase["schur_factor"][0] / max(1, phase["schur_factor"][1])
-    achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
-    # per-kernel split of the same profile: the roofline object describes the kernel with the largest share of the step
-    fams = []
-    for code, kname in ((10, "dgemm_dmma_kernel (cp.async-fed DMMA GEMM: congruences, Gram products, TRSM, edge strips)"),
-                        (11, "dgemm_dmma_bulk_kernel (TMA-fed DMMA GEMM: Schur SYRK, Cholesky trailing updates, large congruences)"),
-                        (12, "panel_rotate_kernel (TMA-fed DMMA panel rotation of the block-Jacobi SVD)")):
-        fm, ff, fn = C.c_double(), C.c_double(), C.c_int64()
-        L.lrn_dbg_gemm_profile(code, C.byref(fm), C.byref(ff), C.byref(fn))
-        if fn.value > 0 and fm.value > 0:
-            fams.append(dict(kernel=kname, launches=int(fn.value), kernel_ms_per_step=fm.value / prof_steps,
-                             algorithmic_flops_per_launch=ff.value / fn.value,
-                             avg_launch_us=1e3 * fm.value / fn.value, achieved=ff.value / (fm.value * 1e-3) / 1e12))
+    e2e_val = t_e2e / (args.steps * units)
+    fams = res["fams"]
     dom = max(fams, key=lambda d: d["kernel_ms_per_step"]) if fams else None
+    phase = res["phase"]
     line = dict(
-        metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-        ms_per_step=1e3 * t_dev / args.steps, higher_is_better=False, scaling="strong" if sharded else "weak", vs_baseline=None,
-        dtype="f64", data="synthetic",
+        metric=METRIC, value=sec_per_iter, unit=UNIT, n_gpus=world, steps=args.steps, warmup=res["warm"],
+        ms_per_step=1e3 * t_dev / args.steps, higher_is_better=False, scaling="strong" if (run.sharded or world == 1) else "weak",
+        vs_baseline=None, dtype="f64", data="synthetic",
         config=dict(workload=workload_name(args.workload), n_var=md.n, msizes=md.msizes[:4], nlin=md.nlin,
-                    options=cfg["options"], l2="inputs larger than L2 (every dense operand is 200 MB; 21 resident m x m matrices)",
-                    parallelism=("schur assembly + Cholesky sharded block-cyclic over %d GPUs (NCCL panel broadcast), rest replicated" % world)
-                    if sharded else ("replicas only" if world > 1 else "single GPU")),
-        e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=e2e_steps),
-        gpu_launches=int(launches),
-        clocks=clocks,
-        solve=solve_info,
+                    options=run.cfg["options"],
+                    l2="inputs larger than L2 (Schur matrix and factor: 12.8 GB each; the dense m x m operands are re-read from HBM "
+                       "between kernels)" if md.n >= 20000 else "inputs larger than L2 (every dense operand of the iteration exceeds 126 MB "
+                       "in total; 19+ resident m x m matrices per block)",
+                    parallelism=("Schur assembly + Cholesky sharded row-block-cyclic over %d GPUs (diagonal-block inverse broadcast, "
+                                 "ncclAllGather of the solved panel, NCCL over NVLink), m x m work replicated" % world)
+                    if run.sharded else ("replicas only" if world > 1 else "single GPU")),
+        e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=res["h2d"], d2h_bytes_per_step=res["h2d"], steps=args.steps),
+        gpu_launches=res["launches"], clocks=res["clocks"], solve=res["solve"],
         phases_ms_per_iteration={k: v[0] / args.steps for k, v in phase.items()},
-        # CUDA-event time of the ABI calls of one step on the library stream (nested phases svd / eigmin not double counted);
-        # `value` is the host clock around the same steps between device synchronisations and also contains the host logic
+        # CUDA-event time of the ABI calls of one step on the library stream (nested phases svd / eigmin not double counted)
         device_event_ms_per_step=sum(v[0] for k, v in phase.items() if k not in ("svd", "eigmin")) / args.steps,
-        schur=dict(assemble_ms=asm_ms, assemble_tflops=alg["assemble"] / (asm_ms * 1e-3) / 1e12 if asm_ms > 0 else None,
-                   factor_ms=fac_ms, factor_tflops=alg["factor"] / (fac_ms * 1e-3) / 1e12 if fac_ms > 0 else None,
-                   assemble_plus_factor_tflops=(alg["assemble"] + alg["factor"]) / ((asm_ms + fac_ms) * 1e-3) / 1e12
-                   if asm_ms + fac_ms > 0 else None),
+        schur=res["schur"],
         roofline=dict(bound="tensor", kernel=dom["kernel"] if dom else None,
                       achieved=dom["achieved"] if dom else None, peak=peak.value, unit="TFLOP/s",
                       frac=dom["achieved"] / peak.value if dom and peak.value else None,
-                      # DRAM bytes per launch from the ncu --set full capture of the same shape (profiles/r1c_svd_round_ncu_full.csv:
-                      # 212.7 MB read + 161.1 MB written; algorithmic: 200 MB read + 200 MB written incl. padding rows)
-                      traffic=373.8e6 if dom and dom["kernel"].startswith("panel_rotate") and args.workload == "C2" else None,
+                      traffic=None,   # no dram__bytes capture of this launch mix is kept for this round; see profiles/ for per-kernel ncu
                       launches_profiled=dom["launches"] if dom else 0, kernel_ms_per_step=dom["kernel_ms_per_step"] if dom else None,
                       avg_launch_us=dom["avg_launch_us"] if dom else None,
                       algorithmic_flops_per_launch=dom["algorithmic_flops_per_launch"] if dom else None,
-                      all_dmma_kernels=dict(achieved=achieved, launches=int(nl.value), kernel_ms_per_step=ms.value / prof_steps),
+                      all_dmma_kernels=dict(achieved=res["all_dmma"]["flops"] / (res["all_dmma"]["ms"] * 1e-3) / 1e12
+                                            if res["all_dmma"]["ms"] > 0 else None,
+                                            launches=res["all_dmma"]["launches"], kernel_ms_per_step=res["all_dmma"]["ms"]),
                       by_kernel=fams,
                       peak_source="measured in this run: register-resident mma.sync.m8n8k4.f64 loop on all SMs "
                                   "(MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.4 TFLOP/s)"),
-        stats=s.stats(),
+        stats=res["stats"], dist_parity=parity,
     )
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(pkg, args)
+    # ---- single-GPU sub-records of the other named configs (N = 1 only) ----------------------------------------------
+    if world == 1 and not args.no_sub and args.workload == "C5":
+        run.s.close()
+        del run
+        subs = {}
+        sub_args = argparse.Namespace(**vars(args))
+        sub_args.steps = min(args.steps, 4)
+        for w in ("C2", "C3", "C4"):
+            r = Runner(pkg, w, local, sharded=False)
+            m = measure(r, sub_args, 1, 0, barrier, None, L, want_solve=not args.no_solve)
+            f2 = max(m["fams"], key=lambda d: d["kernel_ms_per_step"]) if m["fams"] else None
+            subs[w] = dict(workload=workload_name(w), value=m["t_dev"] / sub_args.steps, unit=UNIT, steps=sub_args.steps, warmup=m["warm"],
+                           e2e=m["t_e2e"] / sub_args.steps, gpu_launches=m["launches"], solve=m["solve"], schur=m["schur"],
+                           phases_ms_per_iteration={k: v[0] / sub_args.steps for k, v in m["phase"].items()},
+                           dominant_dmma_kernel=dict(kernel=f2["kernel"], achieved_tflops=f2["achieved"],
+                                                     frac=f2["achieved"] / peak.value if peak.value else None,
+                                                     kernel_ms_per_step=f2["kernel_ms_per_step"]) if f2 else None,
+                           stats=m["stats"])
+            r.s.close()
+            del r
+        line["sub_records"] = subs
+    if world == 1 and not args.no_cpu_baseline:
+        raw, note, cores, phases = cpu_iterations(pkg, args.workload, 0, 1)
+        line["cpu_baseline"] = dict(value=raw, unit=UNIT, cores=cores, kind="port", sample=note, same_config=True,
+                                    phases_s_per_iteration=phases)
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(pkg, args):
-    """oracle (kind "port") timed on this box's host cores on a bounded sample of the same workload"""
-    from oracle import loraine_oracle as lo, sdpa_io
-    blas_threads = use_all_host_threads()
-    cfg = pkg.problems.CONFIGS[args.workload]
-    scale, note = 1.0, "full-size instance"
-    if args.workload == "C2":
-        rows, cols = 25, max(4, args.cpu_sample_n // 25)
-        arrays = pkg.problems.maxcut_torus(rows, cols, 5000)
-        scale = (5000.0 / (rows * cols)) ** 3
-        note = (f"1 IP iteration (after 1 warm-up iteration) of the same generator at torus {rows}x{cols} (n = m = {rows * cols}); all phases are "
-                f"O(n^3): seconds scaled by (5000/{rows * cols})^3 = {scale:.0f} to the full size (explicit extrapolation)")
-    elif args.workload == "C5":
-        ns = 4000
-        arrays = pkg.problems.large_schur(1000, ns, 40000)
-        scale = (40000.0 / ns) ** 3
-        note = (f"1 IP iteration (after 1 warm-up iteration) of the same generator at reduced n_var = {ns} (m = 1000 kept); the "
-                f"iteration is dominated by the n_var^3/3 Cholesky and the O(n_var^2) pair assembly: seconds scaled by "
-                f"(40000/{ns})^3 = {scale:.0f} (explicit extrapolation, upper estimate)")
-    else:
-        arrays = cfg["gen"]()
-    o = dict(cfg["options"], verb=0)
-    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=int(o.get("datarank", 0)), kappa=int(o.get("datasparsity", 8)))
-    s, ha = lo.load(md, o)
-    lo.setup_solver(s, ha)
-    lo.initial_point(s)
-    lo.myIPstep(s, ha)
-    lo.check_convergence(s)
-    t0 = time.perf_counter()
-    lo.myIPstep(s, ha)
-    lo.check_convergence(s)
-    raw = time.perf_counter() - t0
-    return dict(value=raw * scale, unit=UNIT, cores=blas_threads, kind="port", sample=note, measured_s_per_iteration_on_sample=raw)
 
 
 if __name__ == "__main__":

@@ -70,7 +70,26 @@ int32_t lrn_set_b(lrn_handle_t h, const double* b);
 /* builds the device-side sparse structures; must be called once after the setters */
 int32_t lrn_finalize(lrn_handle_t h);
 int32_t lrn_destroy(lrn_handle_t h);
+/* problem dimensions of a handle (a host that loaded the model with lrn_load_sdpa has no other way to know them):
+ * msizes (optional) receives nlmi block sizes */
+int32_t lrn_get_dims(lrn_handle_t h, int64_t* n_var, int64_t* nlmi, int64_t* nlin, int64_t* msizes);
 const char* lrn_last_error(lrn_handle_t h);
+
+/* ---- model preparation inside the library (replaces the per-nonzero triplet builder of MOI.copy_to, src/MOI_wrapper.jl:152-209,
+ * and _prepare_A / prep_AA! / prep_B / prep_sparse!, src/model.jl:120-229) ----
+ * Triplets in SDPA convention: problem  min c'y  s.t.  sum_k F_k y_k - F_0 >= 0 ; entry t says F_{tk[t]} (0 = F_0) has value
+ * tv[t] at (ti[t], tj[t]) (1-based, ONE triangle given, mirrored by the library) of block tblk[t] (1-based); blocksizes[b] > 0 is
+ * a PSD block, < 0 a diagonal (LP) block of -blocksizes[b] rows.  The handle comes back finalized (no lrn_set_* / lrn_finalize
+ * calls needed).  opt->datarank = -1 runs the rank-one conversion of prep_B and fails with LRN_ERR_ARG when a matrix is not
+ * rank one within 5e-6 (the reference throws).  ngpus: 1 = one device, otherwise as lrn_create_multi. */
+int32_t lrn_create_from_triplets(lrn_handle_t* out, int64_t n_var, int64_t nblocks, const int64_t* blocksizes, int64_t ntrip,
+                                 const int64_t* tk, const int64_t* tblk, const int64_t* ti, const int64_t* tj, const double* tv,
+                                 const double* c, const lrn_options_t* opt, int32_t ngpus);
+/* the same from an SDPA sparse file (.dat-s), as examples/solve_sdpa.jl:14-34 does through MOI.FileFormats.SDPA */
+int32_t lrn_load_sdpa(lrn_handle_t* out, const char* path, const lrn_options_t* opt, int32_t ngpus);
+/* find_initial!, src/initial_point.jl:17-81: X_i = Eps_i I, S_i = Eta_i I, y = 0, x_lin = Epss, s_lin = Etaa on the device
+ * (the norms of the model data it needs are recorded by lrn_finalize); initpoint as in DEFAULT_OPTIONS */
+int32_t lrn_initial_point(lrn_handle_t h, int32_t initpoint);
 
 /* ---- iterate upload / download (initial_point.jl output in; MOI getters out, src/MOI_wrapper.jl:315-354) ---- */
 int32_t lrn_set_iterate(lrn_handle_t h, const double* const* X, const double* const* S, const double* y,

@@ -36,6 +36,13 @@ int32_t lrn_dbg_peak(int32_t kind, double* value);
  * block-Jacobi panel-rotation kernel alone */
 int32_t lrn_dbg_gemm_profile(int32_t mode, double* ms, double* flops, int64_t* launches);
 
+/* test hook (runs WITHOUT a device): the host-side model preparation of lrn_create_from_triplets; hands one prepared matrix back
+ * as 0-based CSC.  which: 0 = AA_iblk (n_var x m^2), 1 = C_iblk (m x m), 2 = B_iblk (n_var x m, datarank = -1), 3 = C_lin
+ * (n_var x nlin); vec_out (optional) receives b (which 0..2) or d_lin (which 3).  Returns the number of stored entries or < 0. */
+int64_t lrn_dbg_model_block(int64_t n_var, int64_t nblocks, const int64_t* blocksizes, int64_t ntrip, const int64_t* tk,
+                            const int64_t* tblk, const int64_t* ti, const int64_t* tj, const double* tv, const double* c,
+                            int32_t datarank, int64_t iblk, int32_t which, int64_t cap, int64_t* colptr_out, int64_t* rowval_out,
+                            double* nzval_out, double* vec_out);
 /* test hook: give a single-GPU handle the Schur-row ownership of `rank` out of `world` (row blocks of `block_rows` rows, 0 =
  * the library's default for n_var) WITHOUT a communicator: lrn_schur_assemble then fills only the owned row blocks, so a test
  * on one GPU can check that the shards of all ranks add up to the full matrix.  lrn_schur_factor refuses to run in that state. */

@@ -44,6 +44,7 @@ def lib():
         "lrn_set_b": (i32, [vp, pdbl]),
         "lrn_finalize": (i32, [vp]),
         "lrn_destroy": (i32, [vp]),
+        "lrn_get_dims": (i32, [vp, pi64, pi64, pi64, pi64]),
         "lrn_last_error": (C.c_char_p, [vp]),
         "lrn_set_iterate": (i32, [vp, ppd, ppd, pdbl, pdbl, pdbl]),
         "lrn_get_solution": (i32, [vp, pdbl, ppd, pdbl]),
@@ -68,6 +69,16 @@ def lib():
         "lrn_kernel_launches": (i64, []),
         "lrn_stats": (i32, [vp, pi64]),
         "lrn_set_option": (i32, [vp, C.c_char_p, dbl]),
+        "lrn_create_from_triplets": (i32, [C.POINTER(vp), i64, i64, pi64, i64, pi64, pi64, pi64, pi64, pdbl, pdbl,
+                                           C.POINTER(lrn_options_t), i32]),
+        "lrn_load_sdpa": (i32, [C.POINTER(vp), C.c_char_p, C.POINTER(lrn_options_t), i32]),
+        "lrn_initial_point": (i32, [vp, i32]),
+        "lrn_create_multi": (i32, [C.POINTER(vp), i64, i64, pi64, i64, C.POINTER(lrn_options_t), i32, pi32]),
+        "lrn_dbg_set_shard": (i32, [vp, i32, i32, i32]),
+        "lrn_dbg_model_block": (i64, [i64, i64, pi64, i64, pi64, pi64, pi64, pi64, pdbl, pdbl, i32, i64, i32, i64, pi64, pi64, pdbl,
+                                      pdbl]),
+        "lrn_dbg_compare": (i32, [vp, vp, i32, pdbl]),
+        "lrn_dbg_gather_H": (i32, [vp]),
         "lrn_dist_unique_id": (i32, [C.c_char_p]),
         "lrn_dist_init": (i32, [vp, i32, i32, C.c_char_p]),
     }
@@ -85,4 +96,9 @@ DECLARED_SYMBOLS = ["lrn_default_options", "lrn_create", "lrn_set_block_AA", "lr
                     "lrn_schur_assemble", "lrn_rhs_predictor", "lrn_rhs_corrector", "lrn_schur_factor", "lrn_schur_shift",
                     "lrn_schur_solve", "lrn_prec_prepare", "lrn_pcg", "lrn_find_step", "lrn_sigma_trace", "lrn_dimacs",
                     "lrn_get_array", "lrn_apply_operator", "lrn_timers", "lrn_kernel_launches", "lrn_stats", "lrn_set_option",
-                    "lrn_dist_unique_id", "lrn_dist_init"]
+                    "lrn_dist_unique_id", "lrn_dist_init", "lrn_create_multi",
+                    "lrn_create_from_triplets", "lrn_load_sdpa", "lrn_initial_point", "lrn_get_dims"]
+
+DEBUG_SYMBOLS = ["lrn_dbg_gemm", "lrn_dbg_cholesky", "lrn_dbg_eig_small", "lrn_dbg_svd", "lrn_dbg_lanczos",
+                 "lrn_dbg_batched_lambda_min", "lrn_dbg_peak", "lrn_dbg_gemm_profile", "lrn_dbg_set_shard", "lrn_dbg_compare",
+                 "lrn_dbg_gather_H", "lrn_dbg_model_block"]

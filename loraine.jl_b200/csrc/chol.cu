@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void zero_upper_kernel(double* A, int n, int lda) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y;
-    if (i < n && i < j) A[(size_t)j * lda + i] = 0.0;
+    int j = blockIdx.y + gridDim.y * blockIdx.z;        // y/z split: n may exceed the 65535 limit of grid.y
+    if (j < n && i < n && i < j) A[(size_t)j * lda + i] = 0.0;
 }
 
 }  // namespace
@@ -646,7 +646,8 @@ void trsm_left_lower_trans(const double* L, int n, int lda, const CholWork& work
 
 void zero_strict_upper(double* A, int n, int lda, cudaStream_t st) {
     if (n <= 1) return;
-    dim3 grid((unsigned)cdiv(n, 256), (unsigned)n);
+    const unsigned gy = (unsigned)std::min(n, 32768);
+    dim3 grid((unsigned)cdiv(n, 256), gy, (unsigned)cdiv(n, gy));
     zero_upper_kernel<<<grid, 256, 0, st>>>(A, n, lda);
     LRN_CHECK_LAUNCH();
 }

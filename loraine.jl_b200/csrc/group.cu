@@ -3,6 +3,7 @@
 #include "group.cuh"
 #include "dist.cuh"
 #include <cmath>
+#include <algorithm>
 
 #include "../../include/loraine_b200_debug.h"
 
@@ -11,7 +12,8 @@ using namespace lrn;
 namespace {
 // acc[0] += sum (a - b)^2, acc[1] += sum b^2 over the lower triangle
 __global__ void k_lower_diff(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int n, double* acc) {
-    const int j = blockIdx.y;
+    const int j = blockIdx.y + gridDim.y * blockIdx.z;
+    if (j >= n) return;
     double d2 = 0.0, b2 = 0.0;
     for (int i = j + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double a = A[(size_t)j * lda + i], b = B[(size_t)j * ldb + i];
@@ -104,7 +106,8 @@ int32_t lrn_dbg_compare(lrn_handle_t a, lrn_handle_t b, int32_t which, double* r
         LRN_CUDA(cudaStreamSynchronize(b->st));
         DevBuf<double> acc(2);
         const int n = a->n_var;
-        dim3 grid(8, (unsigned)n);
+        const unsigned gy = (unsigned)std::min(n, 32768);
+        dim3 grid(8, gy, (unsigned)cdiv(n, gy));
         k_lower_diff<<<grid, 256, 0, a->st>>>(Ma.p(), Ma.ld, Mb.p(), Mb.ld, n, acc.p);
         LRN_CHECK_LAUNCH();
         double hst[2] = {0, 0};

@@ -100,9 +100,10 @@ __global__ void k_coldot(int rows, int cols, const double* A, int lda, const dou
     s = warp_sum(s);
     if (lane == 0) d[warp] = s;
 }
+// columns are spread over blockIdx.y and blockIdx.z so that n_var may exceed the 65535 limit of grid.y
 __global__ void k_mirror_lower(int n, double* A, int lda) {
-    int i = blockIdx.x * TB + threadIdx.x, j = blockIdx.y;
-    if (i < n && i > j) A[(size_t)i * lda + j] = A[(size_t)j * lda + i];
+    int i = blockIdx.x * TB + threadIdx.x, j = blockIdx.y + gridDim.y * blockIdx.z;
+    if (j < n && i < n && i > j) A[(size_t)i * lda + j] = A[(size_t)j * lda + i];
 }
 __global__ void k_vec_op(int n, int op, double* out, const double* a, const double* b) {
     int i = blockIdx.x * TB + threadIdx.x;
@@ -451,7 +452,8 @@ void mat_coldot(cudaStream_t st, int rows, int cols, const double* A, int lda, c
 }
 void mat_mirror_lower(cudaStream_t st, int n, double* A, int lda) {
     if (n <= 1) return;
-    k_mirror_lower<<<grid2(n, n), TB, 0, st>>>(n, A, lda);
+    const unsigned gy = (unsigned)std::min(n, 32768);
+    k_mirror_lower<<<dim3((unsigned)cdiv(n, TB), gy, (unsigned)cdiv(n, gy)), TB, 0, st>>>(n, A, lda);
     LRN_CHECK_LAUNCH();
 }
 void vec_op(cudaStream_t st, int n, VecOp op, double* out, const double* a, const double* b) {

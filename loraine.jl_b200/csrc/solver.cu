@@ -10,6 +10,10 @@
 
 using namespace lrn;
 
+namespace lrn {
+void record_model_norms(lrn_solver* h, const std::vector<double>& b_host);   // model.cu
+}
+
 namespace {
 
 constexpr int TBK = 256;
@@ -389,7 +393,8 @@ int32_t lrn_create(lrn_handle_t* out, int64_t n_var, int64_t nlmi, const int64_t
             h->err = "loraine_b200 requires an sm_100 (Blackwell) GPU; there is no fallback path";
             return LRN_ERR_NO_DEVICE;
         }
-        LRN_REQUIRE(n_var >= 1 && n_var < 65535, "n_var out of range (1..65534)");
+        // the Schur matrix and its factor are dense n_var x n_var FP64 (2 x 8 n_var^2 bytes): 140 000 is what 180 GB of HBM holds
+        LRN_REQUIRE(n_var >= 1 && n_var <= 140000, "n_var out of range (1..140000)");
         LRN_REQUIRE(nlmi >= 0 && nlin >= 0 && nlin < 2000000000LL, "nlmi/nlin out of range");
         LRN_REQUIRE(nlmi == 0 || msizes, "msizes is null");
         h->n_var = (int)n_var; h->nlmi = (int)nlmi; h->nlin = (int)nlin;
@@ -452,6 +457,7 @@ int32_t lrn_set_b(lrn_handle_t h, const double* b) {
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(b, "b is null");
         h->b.upload(b, h->n_var, h->st);
+        h->hb.assign(b, b + h->n_var);
         double s = 0;
         for (int j = 0; j < h->n_var; j++) s += b[j] * b[j];
         h->normb = std::sqrt(s);
@@ -467,6 +473,7 @@ int32_t lrn_finalize(lrn_handle_t h) {
         LRN_REQUIRE(h->b.p, "lrn_set_b was not called");
         const int n = h->n_var;
         int maxm = 1;
+        record_model_norms(h, h->hb);          // norms of AA_i, b, C_lin rows for lrn_initial_point (host copies still exist)
         for (auto& B : h->blk) { build_block(h, B); maxm = std::max(maxm, B.m); }
         if (h->nlin > 0) {
             LRN_REQUIRE(h->hClin.set, "lrn_set_lin was not called");
@@ -580,6 +587,16 @@ int32_t lrn_destroy(lrn_handle_t h) {
     if (h->nccl) { delete static_cast<DistCtx*>(h->nccl); h->nccl = nullptr; }
     delete h;
     if (st) cudaStreamDestroy(st);
+    return LRN_OK;
+}
+
+int32_t lrn_get_dims(lrn_handle_t h, int64_t* n_var, int64_t* nlmi, int64_t* nlin, int64_t* msizes) {
+    if (!h) return LRN_ERR_ARG;
+    if (h->group) return lrn_get_dims(static_cast<Group*>(h->group)->members[0], n_var, nlmi, nlin, msizes);
+    if (n_var) *n_var = h->n_var;
+    if (nlmi) *nlmi = h->nlmi;
+    if (nlin) *nlin = h->nlin;
+    if (msizes) for (int i = 0; i < h->nlmi; i++) msizes[i] = h->blk[i].m;
     return LRN_OK;
 }
 
@@ -919,7 +936,9 @@ int32_t lrn_schur_factor(lrn_handle_t h) {
             Phase ph(h, LRN_T_FACTOR);
             cudaStream_t st = h->st;
             LRN_CUDA(cudaMemcpyAsync(h->L.p(), h->H.p(), h->H.bytes(), cudaMemcpyDeviceToDevice, st));
-            if (h->world > 1)
+            LRN_REQUIRE(h->world <= 1 || (h->nccl && static_cast<DistCtx*>(h->nccl)->comm),
+                        "the Schur rows are sharded but the handle has no NCCL communicator (lrn_dist_init / lrn_create_multi)");
+            if (h->nccl && static_cast<DistCtx*>(h->nccl)->comm)
                 cholesky_dist(h->L.p(), h->n_var, h->L.ld, h->cholH, *static_cast<DistCtx*>(h->nccl), h->dist_pw, st);
             else
                 cholesky_lower(h->L.p(), h->n_var, h->L.ld, h->cholH, st);

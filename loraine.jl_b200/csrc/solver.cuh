@@ -66,6 +66,11 @@ struct lrn_solver {
     lrn::DevBuf<double> b, d_lin, y, dely, rhs, Rp, tn1, tn2, ones;
     lrn::DevBuf<double> x_lin, s_lin, si_lin, dx_lin, ds_lin, xn_lin, sn_lin, rnt_lin, rd_lin, tl1, tl2;
     double normb = 0.0, normd = 0.0;
+    // model norms kept for lrn_initial_point (src/initial_point.jl:28-71): ||AA_i||_F, ||1 + |b|||, max_j (1+|b_j|)/(1+||C_lin[j,:]||),
+    // max_j ||C_lin[j,:]||
+    std::vector<double> hb, ip_normAA;
+    double ip_normb2 = 0.0, ip_pmax = 0.0, ip_rownmax = 0.0;
+    bool ip_ready = false;
     lrn::DMat H, L, BG;
     lrn::CholWork cholH;
     bool have_factor = false;

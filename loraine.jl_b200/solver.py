@@ -17,7 +17,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from . import _lib
-from .model import MyModel, RawProblem, prepare_model
+from .model import MyModel, RawProblem, prepare_model, raw_from_sdpa_arrays
 
 # src/Solvers.jl:169-185
 DEFAULT_OPTIONS = {
@@ -86,7 +86,7 @@ class MySolver:
         self.cg_iter_tot = 0
         self.trace = []
         self.status = 0
-        self.extra = {k: o[k] for k in ("svd_tol", "lanczos_tol", "schur_split", "device") if k in o}
+        self.extra = {k: o[k] for k in ("svd_tol", "lanczos_tol", "schur_split", "device", "ngpus") if k in o}
 
     # -- plumbing ---------------------------------------------------------------------------------------------------
     def _err(self):
@@ -223,7 +223,16 @@ def setup_solver(s: MySolver, halpha: Halpha):
     opt.lanczos_tol = float(s.extra.get("lanczos_tol", 0.0))
     opt.device = int(s.extra.get("device", -1))
     ms = np.array(md.msizes, dtype=np.int64)
-    rc = lib.lrn_create(C.byref(s.h), md.n, md.nlmi, _ip(ms) if md.nlmi else None, md.nlin, C.byref(opt))
+    if getattr(s, "sdpa_arrays", None) is not None:
+        _setup_native(s, opt)
+        return
+    if s.h:                                    # a second setup_solver on the same object (solve() after a manual set-up)
+        s.close()
+    ngpus = int(s.extra.get("ngpus", 1))
+    if ngpus != 1:                             # one host thread, N devices: the library owns the NCCL communicators
+        rc = lib.lrn_create_multi(C.byref(s.h), md.n, md.nlmi, _ip(ms) if md.nlmi else None, md.nlin, C.byref(opt), ngpus, None)
+    else:
+        rc = lib.lrn_create(C.byref(s.h), md.n, md.nlmi, _ip(ms) if md.nlmi else None, md.nlin, C.byref(opt))
     if rc != 0:
         msg = s._err() if s.h else "no usable sm_100 CUDA device"
         raise LoraineB200Error(f"lrn_create failed ({rc}): {msg}; there is no CPU fallback")
@@ -241,6 +250,25 @@ def setup_solver(s: MySolver, halpha: Halpha):
     s._call("lrn_finalize")
 
 
+def _setup_native(s, opt):
+    """Model preparation inside the library (lrn_create_from_triplets: the bulk replacement of MOI.copy_to's triplet builder
+    and of _prepare_A, src/MOI_wrapper.jl:152-209, src/model.jl:120-229): the SDPA triplets go down as they are."""
+    n, bs, c, body = s.sdpa_arrays
+    body = np.asarray(body, dtype=np.float64).reshape(-1, 5)
+    tk, tb, ti, tj = (np.ascontiguousarray(body[:, k], dtype=np.int64) for k in range(4))
+    tv = np.ascontiguousarray(body[:, 4], dtype=np.float64)
+    bsa = np.array(bs, dtype=np.int64)
+    cc = np.ascontiguousarray(c, dtype=np.float64)
+    if s.h:
+        s.close()
+    rc = s.lib.lrn_create_from_triplets(C.byref(s.h), int(n), len(bs), _ip(bsa), tv.shape[0], _ip(tk), _ip(tb), _ip(ti), _ip(tj),
+                                        _dp(tv), _dp(cc), C.byref(opt), int(s.extra.get("ngpus", 1)))
+    if rc != 0:
+        msg = s._err() if s.h else "model preparation failed (see stderr)"
+        raise LoraineB200Error(f"lrn_create_from_triplets failed ({rc}): {msg}; there is no CPU fallback")
+    s.native_model = True
+
+
 def _set_csc(s, fname, i, M):
     cp, rv, nz = _csc_args(M)    # locals keep the numpy buffers alive for the duration of the call
     s._call(fname, i, _ip(cp), _ip(rv), _dp(nz))
@@ -249,6 +277,11 @@ def _set_csc(s, fname, i, M):
 def initial_point(s: MySolver):
     """src/initial_point.jl:1-81 (host: a few norms of the model data), then upload."""
     md = s.model
+    if getattr(s, "native_model", False):
+        # find_initial! on the device from the norms recorded by lrn_finalize (no host copy of the model needed)
+        s._call("lrn_initial_point", int(s.initpoint))
+        s.sigma, s.tau, s.expon, s.DIMACS_error, s.iter, s.status = 3.0, 0.95, 3.0, 1.0, 0, 0
+        return
     n = md.b.shape[0]
     y = np.zeros(n)
     b2 = 1 + np.abs(md.b)
@@ -499,19 +532,24 @@ def myIPstep(s, halpha):
     find_mu(s)
     prepare_W(s)
     predictor(s, halpha)
-    if s.status == 3 and s.kit == 0 and not hasattr(s, "cholBBBB"):
+    if s.status == 3:
+        # H could not be made positive definite (src/predictor_corrector.jl:66-70, :76-83): the reference carries on with
+        # cholBBBB = I for the rest of this iteration and leaves the loop at src/Solvers.jl:336; there is no factor on the
+        # device, so the iteration ends here with the same status (INFEASIBLE_OR_UNBOUNDED)
         return
     sigma_update(s)
     corrector(s, halpha)
 
 
-def solve(s: MySolver, halpha: Halpha, max_iters=None):
-    """src/Solvers.jl:304-361."""
+def solve(s: MySolver, halpha: Halpha, max_iters=None, setup=True):
+    """src/Solvers.jl:304-361.  setup=False keeps the device handle of an earlier setup_solver (e.g. one that was attached to
+    an NCCL communicator with dist.init_distributed) and only restarts from the initial point."""
     t1 = time.perf_counter()
     if s.verb > 0:
         print(" *** IP STARTS")
         print(" it        obj         error     CPU/it" if s.kit == 0 else " it        obj         error     cg_iter   CPU/it")
-    setup_solver(s, halpha)
+    if setup or not s.h:
+        setup_solver(s, halpha)
     initial_point(s)
     while s.status == 0:
         t2 = time.perf_counter()
@@ -559,7 +597,7 @@ class Optimizer:
         self.silent = False
 
     def set_attribute(self, name, value):
-        if name not in DEFAULT_OPTIONS and name not in ("svd_tol", "lanczos_tol", "schur_split", "device"):
+        if name not in DEFAULT_OPTIONS and name not in ("svd_tol", "lanczos_tol", "schur_split", "device", "ngpus"):
             raise KeyError(f"UnsupportedAttribute: {name}")
         self.options[name] = value
 
@@ -573,6 +611,12 @@ class Optimizer:
         if self.silent:
             opts["verb"] = 0
         self.solver, self.halpha = load(model, opts)
+
+    def load_sdpa(self, n, bs, c, body, max_sense=False):
+        """SDPA arrays (what read_sdpa returns) with the model preparation done INSIDE the library (lrn_create_from_triplets
+        and lrn_initial_point); the host keeps a MyModel only for the objective getters."""
+        self.copy_to(raw_from_sdpa_arrays(n, bs, c, body), max_sense=max_sense)
+        self.solver.sdpa_arrays = (int(n), [int(b) for b in bs], np.asarray(c, float), np.asarray(body, float))
 
     def optimize(self, max_iters=None):
         solve(self.solver, self.halpha, max_iters=max_iters)

@@ -683,6 +683,29 @@ def _chol_lower(H):
         raise PosDefException(str(e))
 
 
+def _chol_lower_inplace(H):
+    """LAPACK dpotrf on the lower triangle of a Fortran-ordered H, in place (no n x n temporaries; the strict upper triangle
+    is left as it was and never read by the triangular solves) -- same factor as _chol_lower."""
+    L, info = sla.lapack.dpotrf(H, lower=1, overwrite_a=1, clean=0)
+    if info != 0:
+        raise PosDefException(f"dpotrf info = {info}")
+    return L
+
+
+def _assemble_lean(s):
+    """kit = 0, datarank != -1 at sizes where the NumPy assembly (makeBBBBsi_entries) and its n x n temporaries take minutes:
+    the lower triangle of the same H = sum_i tr(calA_j W_i calA_k W_i) (+ LP term) from the plain-C restatement
+    oracle/schur_pairs.c, Fortran-ordered, nothing mirrored (`Hermitian(BBBB, :L)` only reads the lower triangle)."""
+    from . import c_oracle
+    md = s.model
+    H = np.zeros((md.n, md.n), order="F")
+    for i in range(md.nlmi):
+        c_oracle.schur_pairs_lower(md.AA[i], md.msizes[i], s.W[i], H=H, accumulate=(i > 0), nthreads=getattr(s, "threads", 0))
+    if md.nlin > 0:
+        H += np.tril(lp_schur(md, s.X_lin * s.S_lin_inv))
+    return H
+
+
 def _timed(s, name, t0):
     s.phase_time[name] = s.phase_time.get(name, 0.0) + (time.perf_counter() - t0)
 
@@ -694,8 +717,8 @@ def _solve_direct(s, h):
     if s.chol_is_factor_object:
         x = sla.cho_solve((s.cholBBBB, True), h)
         return sla.cho_solve((s.cholBBBB, True), x)
-    x = sla.solve_triangular(s.cholBBBB, h, lower=True)
-    return sla.solve_triangular(s.cholBBBB.T, x, lower=False)
+    x = sla.solve_triangular(s.cholBBBB, h, lower=True, check_finite=False)
+    return sla.solve_triangular(s.cholBBBB, x, lower=True, trans="T", check_finite=False)
 
 
 def predictor(s, halpha):
@@ -712,7 +735,12 @@ def predictor(s, halpha):
         s.Rd_lin = md.d_lin - s.S_lin - md.C_lin.T @ s.y
     _timed(s, "residuals", t0)
 
-    if s.kit == 0:
+    lean = bool(getattr(s, "lean", False)) and s.kit == 0 and s.datarank != -1 and md.nlmi > 0
+    if lean:
+        t0 = time.perf_counter()
+        BBBB = _assemble_lean(s)
+        _timed(s, "schur_assemble", t0)
+    elif s.kit == 0:
         t0 = time.perf_counter()
         if md.nlmi > 0:
             if s.datarank == -1:
@@ -740,9 +768,12 @@ def predictor(s, halpha):
     if s.kit == 0:
         t0 = time.perf_counter()
         try:
-            s.cholBBBB = _chol_lower(BBBB)
+            s.cholBBBB = _chol_lower_inplace(BBBB) if lean else _chol_lower(BBBB)
             s.chol_is_factor_object = False
         except PosDefException:
+            if lean:                                              # the in-place attempt destroyed H: form it again
+                BBBB = _assemble_lean(s)
+                BBBB = np.tril(BBBB) + np.tril(BBBB, -1).T
             icount = 0
             s.regcount += 1
             if s.regcount > 5:
@@ -828,6 +859,8 @@ def corrector(s, halpha):
         tmp = (s.delX_lin * s.delS_lin) * s.Si_lin - (s.sigma * s.mu) * s.Si_lin
         h = h + md.C_lin @ ((s.X_lin * s.Si_lin) * s.Rd_lin + s.X_lin + tmp)
     _timed(s, "rhs", t0)
+    if "rhs_corr" in s.hooks:
+        s.hooks["rhs_corr"](s, h)
     if s.kit == 0:
         t0 = time.perf_counter()
         s.dely = _solve_direct(s, h)

@@ -134,3 +134,84 @@ def test_full_size_checker_matches_oracle_assembly(pkg):
     AA = md.AA[0].tocsr()
     err = max(abs(tgs.schur_entry_ref(AA, W, j, k) - H[max(j, k), min(j, k)]) for j in range(0, 200, 7) for k in range(0, 200, 11))
     assert err <= 1e-12 * np.abs(H).max()
+
+
+@pytest.mark.parametrize("name,datarank", [("theta1", 0), ("control1", 0), ("tru3", 0), ("vib3", 0), ("maxcut", -1), ("c4mini", 0)])
+def test_native_model_preparation_matches_the_python_host(pkg, golden_dir, name, datarank):
+    """lrn_create_from_triplets' host side (csrc/model.cu: prep_AA!, C = -A[i,1], prep_B, C_lin / d_lin / b conventions of
+    src/model.jl:120-229 and src/MOI_wrapper.jl:186-217) against model.py on the same SDPA triplets -- no device needed."""
+    import scipy.sparse as sp
+    from loraine_jl_b200 import _lib
+    L = _lib.lib()
+    if name == "maxcut":
+        n, bs, c, body = pkg.problems.maxcut_torus(6, 8, 3)
+    elif name == "c4mini":
+        n, bs, c, body = pkg.problems.multiblock_lp(5, 20, 40, 50)
+    else:
+        z = np.load(os.path.join(golden_dir, name + ".npz"))
+        n, bs, c, body = int(z["n"]), [int(b) for b in z["bs"]], z["c"], z["body"]
+    md = pkg.prepare_model(pkg.raw_from_sdpa_arrays(n, bs, c, body), datarank=datarank, kappa=8)
+    body = np.asarray(body, float).reshape(-1, 5)
+    tk, tb, ti, tj = (np.ascontiguousarray(body[:, k], dtype=np.int64) for k in range(4))
+    tv = np.ascontiguousarray(body[:, 4])
+    bsa = np.array(bs, dtype=np.int64)
+    cc = np.ascontiguousarray(c, dtype=np.float64)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def fetch(iblk, which, shape, veclen):
+        cap = 4 * body.shape[0] + 16
+        colptr = np.zeros(shape[1] + 1, dtype=np.int64)
+        rowval = np.zeros(cap, dtype=np.int64)
+        nzval = np.zeros(cap)
+        vec = np.zeros(max(1, veclen))
+        nnz = L.lrn_dbg_model_block(n, len(bs), ip(bsa), tv.shape[0], ip(tk), ip(tb), ip(ti), ip(tj), dp(tv), dp(cc), datarank,
+                                    iblk, which, cap, ip(colptr), ip(rowval), dp(nzval), dp(vec) if veclen else None)
+        assert nnz >= 0, nnz
+        return sp.csc_matrix((nzval[:nnz], rowval[:nnz], colptr), shape=shape), vec[:veclen]
+
+    def same(A, B):
+        D = (sp.csc_matrix(A) - sp.csc_matrix(B))
+        return (abs(D).max() if D.nnz else 0.0) <= 1e-9 * max(1.0, abs(sp.csc_matrix(B)).max() if sp.csc_matrix(B).nnz else 1.0)
+
+    for i, m in enumerate(md.msizes):
+        AA, b = fetch(i, 0, (n, m * m), n)
+        assert same(AA, md.AA[i]) and AA.nnz == sp.csc_matrix(md.AA[i]).nnz
+        assert np.array_equal(b, md.b)
+        Ci, _ = fetch(i, 1, (m, m), 0)
+        assert same(Ci, md.C[i])
+        if datarank == -1:
+            Bi, _ = fetch(i, 2, (n, m), 0)
+            Bd, Br = Bi.toarray(), md.B[i].toarray()
+            sgn = np.sign(np.sum(Bd * Br, axis=1)); sgn[sgn == 0] = 1          # b_k is defined up to its sign
+            assert np.abs(Bd - sgn[:, None] * Br).max() <= 1e-9
+    if md.nlin:
+        Cl, d = fetch(0, 3, (n, md.nlin), md.nlin)
+        assert same(Cl, md.C_lin) and np.allclose(d, md.d_lin, rtol=0, atol=1e-12)
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    from loraine_jl_b200 import _lib
+    exe = str(tmp_path / "c_abi_host")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["/usr/bin/gcc", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi_host.c"),
+           "-L", libdir, "-lloraine_b200", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_host_compiles_against_the_header_only(pkg, tmp_path):
+    """tests/c_abi_host.c drives a whole solve through include/loraine_b200.h (no torch types, no Python): it must compile as
+    C (not C++) with -Wall -Werror and link against the shared library alone; without a GPU it must fail loudly."""
+    import subprocess
+    import torch
+    exe = _build_c_host(tmp_path)
+    if not torch.cuda.is_available():
+        from loraine_jl_b200 import model as M
+        z = np.load(os.path.join(ROOT, "tests", "golden", "theta1.npz"))
+        path = str(tmp_path / "theta1.dat-s")
+        M.write_sdpa(path, int(z["n"]), [int(b) for b in z["bs"]], z["c"], z["body"])
+        r = subprocess.run([exe, path], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr

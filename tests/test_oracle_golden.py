@@ -138,3 +138,55 @@ def test_large_fixture_records(golden_dir):
     z = np.load(f"{golden_dir}/thetaG11.npz")
     assert abs(float(z["oracle_obj"]) - 400.0) <= 1e-4
     assert int(z["bs"][0]) == 801 and int(z["n"]) == 2401
+
+
+def test_c_restatement_of_sparse_schur_assembly_matches_numpy_oracle(golden_dir):
+    """oracle/schur_pairs.c (plain-C restatement of src/makeBBBB.jl:39-64,139-213, used by the CPU arm of bench.py at
+    n_var = 40000) against the NumPy oracle: the literal as-written loops on a small instance, the vectorised form on the
+    fixtures (multi-block, LP block present), full matrix and a column panel."""
+    from oracle import c_oracle
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    rng = np.random.default_rng(5)
+    arrays = pkg.problems.large_schur(12, 40, 3)
+    md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=0, kappa=8)
+    N = rng.standard_normal((12, 12)); W = N @ N.T + np.eye(12)
+    Hc = c_oracle.schur_pairs_lower(md.AA[0], 12, W)
+    Hw = lo.makeBBBBsi_aswritten(md, 0, W)
+    # (the literal code fills [max, min] in the F3 branch and both triangles in the F1 branch: the lower triangle is complete)
+    assert np.linalg.norm(np.tril(Hc) - np.tril(Hw)) <= 1e-13 * np.linalg.norm(np.tril(Hw))
+    assert np.all(np.triu(Hc, 1) == 0)
+    for name in ("control1", "tru3"):
+        z, raw = _load(golden_dir, name)
+        md = lo.prepare_model(raw, datarank=0, kappa=8)
+        H = np.zeros((md.n, md.n), order="F")
+        Wl = []
+        for i, m in enumerate(md.msizes):
+            N = rng.standard_normal((m, m)); Wl.append(N @ N.T / m + np.eye(m))
+            c_oracle.schur_pairs_lower(md.AA[i], m, Wl[i], H=H, accumulate=(i > 0), nthreads=3)
+        Ho = lo.makeBBBBs(md, Wl)
+        assert np.linalg.norm(np.tril(H) - np.tril(Ho)) <= 1e-13 * np.linalg.norm(np.tril(Ho)), name
+        k0, k1 = md.n // 3, md.n // 3 + 7
+        P = c_oracle.schur_pairs_lower(md.AA[0], md.msizes[0], Wl[0], cols=(k0, k1))
+        Pref = np.tril(lo.makeBBBBsi_entries(md, 0, Wl[0]))[:, k0:k1]
+        assert np.linalg.norm(P - Pref) <= 1e-13 * max(np.linalg.norm(Pref), 1e-300), name
+
+
+def test_lean_large_instance_path_of_the_oracle_is_the_same_algorithm():
+    """bench.py's CPU arm runs the oracle with `lean = True` at n_var = 40000 (C assembly, in-place dpotrf, no n x n
+    temporaries): same iterates as the plain NumPy path."""
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    arrays = pkg.problems.large_schur(40, 260, 40000)
+    out = []
+    for lean in (False, True):
+        o = dict(lo.DEFAULT_OPTIONS, **pkg.problems.CONFIGS["C5-mini"]["options"]); o["verb"] = 0
+        md = lo.prepare_model(sdpa_io.raw_from_sdpa_arrays(*arrays), datarank=0, kappa=8)
+        s, ha = lo.load(md, o)
+        s.lean = lean
+        lo.solve(s, ha)
+        out.append(s)
+    a, b = out
+    assert a.status == b.status == 1 and a.iter == b.iter
+    assert abs(a.primal_obj - b.primal_obj) <= 1e-10 * (1 + abs(a.primal_obj))
+    assert np.linalg.norm(a.y - b.y) <= 1e-8 * np.linalg.norm(a.y)
