@@ -53,6 +53,7 @@ def test_row_block_shards_add_up_to_the_full_schur_matrix(pkg, golden_dir, case)
             o2, _ = make_pair(pkg, arrays, opts)
             g = o2.solver
             S.setup_solver(g, o2.halpha)
+            S.initial_point(g)
             S.set_iterate(g, *it)
             assert g.lib.lrn_dbg_set_shard(g.h, rank, world, br) == 0
             Hr = np.tril(_assembled_H(S, g))
@@ -77,7 +78,7 @@ def _nccl_world1(pkg, g):
     g._call("lrn_dist_init", 0, 1, buf)
 
 
-@pytest.mark.parametrize("shape", [(30, 700), (40, 1100)])
+@pytest.mark.parametrize("shape", [(60, 700), (60, 1100)])
 def test_distributed_cholesky_with_a_world1_communicator(pkg, shape):
     """cholesky_dist (row-block-cyclic: diagonal-block inverse broadcast, batched row solves, all-gather slots, strided-batch
     staircase updates) run with a one-rank NCCL communicator against the single-GPU look-ahead factorisation: same factor,
@@ -143,7 +144,7 @@ def test_full_size_C4_against_the_oracle(pkg):
     assert relerr(H, Ho) <= 1e-11
     del H, Ho
     lo.predictor(s, ora[2])
-    assert relerr(g.get_array("RP"), s.Rp) <= 1e-9
+    assert np.linalg.norm(g.get_array("RP") - s.Rp) <= 1e-9 * (1.0 + np.linalg.norm(s.model.b))
     assert relerr(g.get_array("DELY"), s.dely) <= 1e-7
     assert np.allclose(g.alpha, s.alpha, rtol=1e-6) and np.allclose(g.beta, s.beta, rtol=1e-6)
     assert abs(g.alpha_lin - s.alpha_lin) <= 1e-6 and abs(g.beta_lin - s.beta_lin) <= 1e-6
@@ -156,23 +157,38 @@ def test_full_size_C4_against_the_oracle(pkg):
     g.close()
 
 
-@pytest.mark.parametrize("gen,args", [("multiblock_lp", (3, 12, 10, 7)), ("theta_torus", (6, 8))])
+@pytest.mark.parametrize("gen,args", [("multiblock_lp", (3, 12, 10, 7)), ("maxcut_torus", (6, 8, 3)), ("multiblock_lp", (3, 4, 40, 7))])
 @pytest.mark.parametrize("erank,aamat", [(1, 0), (1, 1), (1, 3), (2, 2), (3, 2), (2, 0)])
 def test_H_alpha_variants_match_the_oracle(pkg, gen, args, erank, aamat):
     """Prec_for_CG_tilS_prep / MyM (src/Solvers.jl:674-904) for every aamat (tau rule :646-655, identity term dropped for
     aamat = 3 :715-739) and for erank > 1 (the slow t = AA kron(U, Z) formula :752-768), with and without an LP block:
-    M^-1 x against the oracle's functor on the same iterate."""
+    M^-1 x against the oracle's functor built from the SAME W (the device's).  aamat = 3 drops tau^2 I, so AAAATtau is
+    C_lin diag(x./s) C_lin' alone: only defined when the LP block has at least n_var independent rows (third instance:
+    12 variables, 40 LP rows); the instances use random weights (no repeated eigenvalues of W: the erank leading
+    eigenvectors must be unique)."""
     from oracle import loraine_oracle as lo
     from loraine_jl_b200 import solver as S
+    full_rank_lp = (gen == "multiblock_lp" and args[2] >= 3 * args[0] * args[1])
+    if aamat == 3 and not full_rank_lp:
+        pytest.skip("aamat = 3 needs an LP block of full row rank (AAAATtau = C_lin D C_lin' must be invertible)")
+    if full_rank_lp and erank >= 3:
+        pytest.skip("erank must stay below m - 1 = 3")
     arrays = getattr(pkg.problems, gen)(*args)
     o = dict(kit=1, preconditioner=1, erank=erank, aamat=aamat, initpoint=1, verb=0, eDIMACS=1e-6)
-    opt, ora = make_pair(pkg, arrays, o)
+    opt, ora = make_pair(pkg, arrays, dict(o, aamat=2 if aamat == 3 else aamat))     # two ordinary iterations first
     g, s = step_both(pkg, opt, ora, 2)
+    g._call("lrn_set_option", b"aamat", float(aamat))
+    s.aamat = aamat
     for mod, st in ((S, g), (lo, s)):
         st.iter += 1; st.cg_iter_pre = st.cg_iter_cor = 0
         mod.find_mu(st); mod.prepare_W(st)
     g._call("lrn_residuals"); g._call("lrn_rhs_predictor"); g._call("lrn_prec_prepare", 1)
     ha = ora[2]
+    # the oracle's factors from the DEVICE's iterate (W, x_lin ./ s_lin): differences are then the algorithm's alone
+    s.W = [g.get_array("W", i) for i in range(s.model.nlmi)]
+    if s.model.nlin:
+        _, _, _, xl, sl = _iterate(S, g)
+        s.X_lin, s.S_lin_inv = xl, 1.0 / sl
     lo.Prec_for_CG_tilS_prep(s, ha)
     rng = np.random.default_rng(erank * 10 + aamat)
     dpx = lambda a: a.ctypes.data_as(PD)
@@ -201,9 +217,10 @@ def test_right_hand_sides_and_residuals_directly(pkg, golden_dir, name, datarank
         st.iter += 1
         st.cg_iter_pre = st.cg_iter_cor = 0
         mod.find_mu(st); mod.prepare_W(st); mod.predictor(st, ha)
-    assert relerr(g.get_array("RP"), s.Rp) <= 1e-9
+    nb = 1.0 + np.linalg.norm(s.model.b)           # Rp tends to zero (primal feasibility): error relative to 1 + ||b|| like err1
+    assert np.linalg.norm(g.get_array("RP") - s.Rp) <= 1e-9 * nb
     for i in range(s.model.nlmi):
-        assert relerr(g.get_array("RD", i), s.Rd[i]) <= 1e-9
+        assert np.linalg.norm(g.get_array("RD", i) - s.Rd[i]) <= 1e-9 * (1.0 + np.linalg.norm(s.model.C[i].toarray()))
     assert relerr(g.get_array("RHS"), got["pred"]) <= 1e-8
     assert abs(S.sigma_update(g) - lo.sigma_update(s)) <= 1e-6
     S.corrector(g, opt.halpha); lo.corrector(s, ora[2])
@@ -218,7 +235,7 @@ def test_in_process_multi_gpu_handle(pkg):
     from loraine_jl_b200 import solver as S
     ndev = torch.cuda.device_count()
     cfg = pkg.problems.CONFIGS["C5-mini"]
-    arrays = pkg.problems.large_schur(30, 700, 40000)
+    arrays = pkg.problems.large_schur(60, 700, 40000)
     res = []
     for ngpus in sorted({1, min(2, ndev), ndev}):
         opt = pkg.Optimizer()

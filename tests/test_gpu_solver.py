@@ -536,6 +536,15 @@ def test_full_size_C5_properties(pkg):
     ref = np.array([schur_entry_ref(AA, W, j, k) for j, k in zip(js, ks)])
     got = H[js, ks]
     assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # north_star tolerance on whole column panels: relative Frobenius error <= 1e-11 against the plain-C restatement of the
+    # reference's pair formula (oracle/schur_pairs.c, pinned to the NumPy oracle in tests/test_oracle_golden.py) for the same W:
+    # the first panel (all 40000 rows), one in the middle and the last one
+    from oracle import c_oracle
+    for k0 in (0, 19968, n - 512):
+        ref_panel = c_oracle.schur_pairs_lower(md.AA[0], m, W, cols=(k0, k0 + 512))
+        got_panel = np.tril(H[:, k0:k0 + 512], -k0)
+        assert relerr(got_panel, ref_panel) <= 1e-11, k0
+        del ref_panel, got_panel
     dev = torch.device("cuda")
     Ht = torch.from_numpy(H).to(dev)
     Lt = torch.tril(torch.from_numpy(g.get_array("L")).to(dev))
