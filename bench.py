@@ -37,6 +37,16 @@ sys.path.insert(0, ROOT)
 METRIC = "sec/IP-iteration"
 UNIT = "s"
 
+# stdout carries exactly ONE line (the JSON record): every other writer to file descriptor 1 (NCCL's version banner, library
+# messages of any rank) is sent to stderr; the record itself goes to a private duplicate of the original stdout
+_RECORD_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RECORD_OUT.write(json.dumps(line) + "\n")
+    _RECORD_OUT.flush()
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -192,7 +202,7 @@ def run_reference(args):
                 config=dict(workload=workload_name(args.workload), sample=note, same_config=True),
                 cpu_baseline=dict(value=raw, unit=UNIT, cores=cores, kind="port", sample=note, phases_s_per_iteration=phases),
                 e2e=dict(value=raw, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -457,7 +467,7 @@ def run_b200(args):
         raw, note, cores, phases = cpu_iterations(pkg, args.workload, 0, 1)
         line["cpu_baseline"] = dict(value=raw, unit=UNIT, cores=cores, kind="port", sample=note, same_config=True,
                                     phases_s_per_iteration=phases)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

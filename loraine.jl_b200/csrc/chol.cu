@@ -250,6 +250,117 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Whole-panel factorisation in ONE cooperative launch: the (rows x w) column panel whose top w x w block is the current
+// diagonal block is factored right-looking in 64-column steps,
+//     step j :  CTA 0 factors + inverts the 64 x 64 diagonal block (registers)          | grid barrier
+//               every row tile below:  P_i <- A_ij inv(L_jj)^T        (64 x 64 x 64 DMMA) | grid barrier
+//               remaining panel columns k > j:  A_ik -= P_i P_k^T      (64 x 64 x 64 DMMA) | grid barrier
+// so that the diagonal block AND the rows below it leave the kernel solved.  Replaces, per panel, the cooperative diagonal
+// kernel + its explicit w x w inverse + memset + the rows x w x w panel GEMM + the copy back (5 dependent launches and an
+// m^3-class inversion on the critical path of mid-size factorisations).  Tiles are staged in shared memory [k][m] with a +4
+// padded stride (conflict-free m8n8k4 fragment loads, same layout as gemm.cu).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PLD = DB + 4;
+constexpr size_t PANEL_SMEM = (size_t)2 * DB * PLD * sizeof(double);
+
+__device__ __forceinline__ void dmma884p(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+// s[k*PLD + i] = G[i + k*ld]  (i < rows, k < cols; zero elsewhere)
+__device__ __forceinline__ void ptile_load(double* s, const double* __restrict__ G, int ld, int rows, int cols) {
+    for (int idx = threadIdx.x; idx < DB * DB; idx += 256) {
+        const int i = idx & 63, k = idx >> 6;
+        s[k * PLD + i] = (i < rows && k < cols) ? G[(size_t)k * ld + i] : 0.0;
+    }
+}
+// acc += A B^T with As[k][m], Bs[k][n]; 8 warps as 2 x 4, warp tile 32 x 16.  Element (i, j, t) of acc is row
+// wm0 + 8 i + (lane >> 2), column wn0 + 8 j + 2 (lane & 3) + t.
+__device__ __forceinline__ void ptile_mma(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][2][2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16, lr = lane >> 2, lk = lane & 3;
+#pragma unroll 4
+    for (int kk = 0; kk < DB; kk += 4) {
+        double a[4], b[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = As[(kk + lk) * PLD + wm0 + i * 8 + lr];
+#pragma unroll
+        for (int j = 0; j < 2; j++) b[j] = Bs[(kk + lk) * PLD + wn0 + j * 8 + lr];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma884p(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    panel_factor_kernel(double* __restrict__ A, int lda, int rows, int w, double* __restrict__ dinv, int* __restrict__ info, int base) {
+    extern __shared__ double sm[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    double* As = sm;
+    double* Bs = sm + DB * PLD;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16, lr = lane >> 2, lk = lane & 3;
+    const int nbj = (w + DB - 1) / DB, nt = (rows + DB - 1) / DB;
+    for (int j = 0; j < nbj; j++) {
+        const int j0 = j * DB, jb = min(DB, w - j0);
+        if (c == 0) potrf64_block(A + (size_t)j0 * lda + j0, lda, jb, dinv + (size_t)j * DB * DB, info, base + j0, sm);
+        __threadfence();
+        grid.sync();
+        // ---- row tiles below the diagonal block of this step: P_i <- A_ij inv(L_jj)^T -------------------------------
+        for (int i = j + 1 + c; i < nt; i += G) {
+            const int i0 = i * DB, ib = min(DB, rows - i0);
+            __syncthreads();
+            ptile_load(As, A + (size_t)j0 * lda + i0, lda, ib, jb);
+            ptile_load(Bs, dinv + (size_t)j * DB * DB, DB, DB, DB);      // Bs[k][b] = inv(L_jj)[b][k]
+            __syncthreads();
+            double acc[4][2][2] = {};
+            ptile_mma(As, Bs, acc);
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 2; y++)
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const int a = wm0 + x * 8 + lr, b = wn0 + y * 8 + lk * 2 + t;
+                        if (a < ib && b < jb) A[(size_t)(j0 + b) * lda + i0 + a] = acc[x][y][t];
+                    }
+        }
+        __threadfence();
+        grid.sync();
+        // ---- the panel columns to the right of step j: A_ik -= P_i P_k^T for block columns k > j, row tiles i >= k -----------
+        const int nk = nbj - 1 - j;
+        if (nk > 0) {
+            const long long ntask = (long long)(nt - 1 - j) * nk;
+            for (long long task = c; task < ntask; task += G) {
+                const int i = j + 1 + (int)(task / nk), k = j + 1 + (int)(task % nk);
+                if (k > i) continue;                                   // block-uniform: above the diagonal of the panel
+                const int i0 = i * DB, k0 = k * DB, ib = min(DB, rows - i0), kb = min(DB, w - k0);
+                __syncthreads();
+                ptile_load(As, A + (size_t)j0 * lda + i0, lda, ib, jb);
+                ptile_load(Bs, A + (size_t)j0 * lda + k0, lda, kb, jb);
+                __syncthreads();
+                double acc[4][2][2] = {};
+                ptile_mma(As, Bs, acc);
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 2; y++)
+#pragma unroll
+                        for (int t = 0; t < 2; t++) {
+                            const int a = wm0 + x * 8 + lr, b = wn0 + y * 8 + lk * 2 + t;
+                            if (a < ib && b < kb) A[(size_t)(k0 + b) * lda + i0 + a] -= acc[x][y][t];
+                        }
+            }
+        }
+        __threadfence();
+        grid.sync();
+    }
+}
+
 constexpr int COOP_MAXN = 512;
 
 int pick_nb(int n) { return n > 8192 ? 512 : 256; }
@@ -259,6 +370,8 @@ void potrf_launch_config() {
     once.run([&] {
         LRN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
         LRN_CUDA(cudaFuncSetAttribute(potrf_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+        LRN_CUDA(cudaFuncSetAttribute(panel_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)std::max(POTRF_SMEM, PANEL_SMEM)));
     });
 }
 
@@ -291,60 +404,35 @@ void copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols
     LRN_CHECK_LAUNCH();
 }
 
-// P (rows x kb, below a factored kb x kb diagonal block Akk) <- P * inv(L_kk)^T, 64 columns at a time (small panels)
-void panel_trsm(double* P, int rows, int kb, const double* Akk, const double* dk, int lda, cudaStream_t st) {
-    for (int j = 0; j < kb; j += DB) {
-        const int jb = (kb - j < DB) ? (kb - j) : DB;
-        double* Pj = P + (size_t)j * lda;
-        if (j > 0) gemm_nt(st, rows, jb, j, -1.0, P, lda, Akk + j, lda, 1.0, Pj, lda);
-        gemm_nt(st, rows, jb, jb, 1.0, Pj, lda, dk + (size_t)(j / DB) * DB * DB, DB, 0.0, Pj, lda);
-    }
+// Factor the kb x kb diagonal block at the top of a column panel AND solve the `rows_below` rows under it, in one cooperative
+// launch (panel_factor_kernel).  `gcap` bounds the grid: all SMs for mid-size matrices (the panel chain is the critical path),
+// a third of them for very large ones (the chain hides behind the trailing update; the panel must not evict its CTAs).
+void factor_panel(double* Akk, int kb, int rows_below, int lda, double* dk, int* info, int base, int gcap, cudaStream_t st) {
+    potrf_launch_config();
+    int rows = kb + (rows_below > 0 ? rows_below : 0);
+    const int nt = (int)cdiv(rows, DB), nbj = (int)cdiv(kb, DB);
+    long long tasks = std::max<long long>(nt - 1, (long long)(nt - 1) * std::max(nbj - 1, 1));
+    int G = (int)std::min<long long>(std::max(gcap, 1), std::max<long long>(tasks, 1));
+    const size_t smem = std::max(POTRF_SMEM, PANEL_SMEM);
+    void* args[] = {&Akk, &lda, &rows, &kb, &dk, &info, &base};
+    LRN_CUDA(cudaLaunchCooperativeKernel((void*)panel_factor_kernel, dim3(G), dim3(256), args, smem, st));
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-// Factor the kb x kb diagonal block at the top of a panel and solve the `rows` rows below it:
-//   large panels: explicit inverse X (from the cooperative kernel) and ONE DMMA GEMM  P <- P X^T (out of place, copied back)
-//   small panels: 64-column TRSM through the inverted diagonal blocks
-// If Pout != null the solved rows are left in Pout (leading dimension ldp) as well.
-void factor_panel(double* Akk, int kb, int rows, int lda, double* dk, int* info, int base, CholWork& work, double* Pout, int ldp,
-                  cudaStream_t st) {
-    const bool useinv = (kb >= 128 && rows >= 512);
-    double* X = nullptr;
-    const int ldx = pad_ld(kb);
-    if (useinv) {
-        if (work.xinv.n < (size_t)ldx * kb) work.xinv.alloc((size_t)ldx * kb);
-        X = work.xinv.p;
-    }
-    potrf_small(Akk, lda, kb, dk, X, ldx, info, base, st);
-    if (rows <= 0) return;
-    double* P = Akk + kb;
-    if (useinv) {
-        double* out = Pout;
-        int ldo = ldp;
-        if (!out) {
-            ldo = pad_ld(rows);
-            if (work.pout.n < (size_t)ldo * kb) work.pout.alloc((size_t)ldo * kb);
-            out = work.pout.p;
-        }
-        gemm_nt(st, rows, kb, kb, 1.0, P, lda, X, ldx, 0.0, out, ldo);
-        copy2d(out, ldo, P, lda, rows, kb, st);
-    } else {
-        panel_trsm(P, rows, kb, Akk, dk, lda, st);
-        if (Pout) copy2d(P, lda, Pout, ldp, rows, kb, st);
-    }
-}
+int panel_grid_cap(int n) { return n >= 16384 ? std::max(16, device_sm_count() / 3) : device_sm_count(); }
 
 void chol_rec(double* A, int n, int lda, double* dinv, int* info, int base, CholWork& work, cudaStream_t st) {
     if (n <= COOP_MAXN) {
         potrf_small(A, lda, n, dinv, nullptr, 0, info, base, st);
         return;
     }
-    const int NB = pick_nb(n);
+    const int NB = pick_nb(n), gcap = panel_grid_cap(n);
     for (int k = 0; k < n; k += NB) {
         const int kb = (n - k < NB) ? (n - k) : NB;
         double* Akk = A + (size_t)k * lda + k;
         double* dk = dinv + (size_t)(k / DB) * DB * DB;
         const int rows = n - k - kb;
-        factor_panel(Akk, kb, rows, lda, dk, info, base + k, work, nullptr, 0, st);
+        factor_panel(Akk, kb, rows, lda, dk, info, base + k, gcap, st);
         if (rows <= 0) break;
         double* P = A + (size_t)k * lda + (k + kb);          // rows x kb panel below the diagonal block
         // trailing update, lower triangle only
@@ -511,12 +599,6 @@ void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int l
     potrf_small(Akk, lda, w, dinv, X, ldx, info, base, st);
 }
 
-void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
-                    int ldp, cudaStream_t st) {
-    factor_panel(Apanel, w, rows - w, lda, dinv, info, base, work, Pout ? Pout + w : nullptr, ldp, st);
-    if (Pout) copy2d(Apanel, lda, Pout, ldp, w, w, st);
-}
-
 void ensure_aux(CholWork& work) {
     if (work.aux) return;
     int lo = 0, hi = 0;
@@ -525,34 +607,34 @@ void ensure_aux(CholWork& work) {
     for (auto& e : work.ev) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
-// Right-looking factorisation with one-step look-ahead on two streams: the latency-bound panel work (cooperative diagonal
-// block kernel + panel solve) of panel p+1 runs on a high-priority side stream while `st` still applies the bulk of the
-// trailing update of panel p.
+// Right-looking factorisation with one-step look-ahead on two streams.  The high-priority panel stream runs the whole
+// dependency chain -- panel p (one cooperative launch: diagonal block + rows below), then the update of the NEXT panel's
+// columns -- while the main stream applies the rest of the trailing update of panel p (columns behind the next panel) on the
+// TMA-fed kernel.  Events: evP[p] "panel p is factored" (main stream may update with it), evR[p] "rest update p is done" (the
+// panel stream may touch the columns it wrote: the next-columns update of step p+1 also receives rest(p)).
 void chol_lookahead(double* A, int n, int lda, CholWork& work, cudaStream_t st) {
     ensure_aux(work);
     cudaStream_t sp = work.aux;
-    cudaEvent_t evStart = work.ev[0], evU = work.ev[1], evF[2] = {work.ev[2], work.ev[3]};
+    cudaEvent_t evStart = work.ev[0], evP[2] = {work.ev[1], work.ev[2]}, evR[2] = {work.ev[3], work.ev[4]};
     int* info = work.info_ptr();
-    const int NB = pick_nb(n), npan = (int)cdiv(n, NB);
+    const int NB = pick_nb(n), npan = (int)cdiv(n, NB), gcap = panel_grid_cap(n);
     LRN_CUDA(cudaEventRecord(evStart, st));
     LRN_CUDA(cudaStreamWaitEvent(sp, evStart, 0));
+    int last = 0;
     for (int p = 0; p < npan; p++) {
         const int c0 = p * NB, w = (n - c0 < NB) ? (n - c0) : NB, rows = n - c0;
         double* Ap = A + (size_t)c0 * lda + c0;
         double* dk = work.dinv.p + (size_t)(c0 / DB) * DB * DB;
-        if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));           // panel p has received the update of panel p-1
-        factor_panel(Ap, w, rows - w, lda, dk, info, c0, work, nullptr, 0, sp);
-        LRN_CUDA(cudaEventRecord(evF[p & 1], sp));
-        LRN_CUDA(cudaStreamWaitEvent(st, evF[p & 1], 0));
+        factor_panel(Ap, w, rows - w, lda, dk, info, c0, gcap, sp);
+        LRN_CUDA(cudaEventRecord(evP[p & 1], sp));
+        last = p & 1;
         const int q0 = c0 + w;
         if (q0 >= n) break;
         const int wq = (n - q0 < NB) ? (n - q0) : NB;
         const double* P = Ap + w;                                           // rows below the diagonal block, lda
-        // next panel column first ...
-        gemm_nt(st, n - q0, wq, w, -1.0, P, lda, P, lda, 1.0, A + (size_t)q0 * lda + q0, lda);
-        LRN_CUDA(cudaEventRecord(evU, st));
-        // ... then the rest of the trailing matrix (lower triangle)
         const int q1 = q0 + wq;
+        // rest of the trailing matrix (lower triangle, columns behind the next panel) on the main stream
+        LRN_CUDA(cudaStreamWaitEvent(st, evP[p & 1], 0));
         if (q1 < n) {
             GemmParams g;
             g.A = P + wq; g.B = P + wq; g.C = A + (size_t)q1 * lda + q1;
@@ -560,7 +642,12 @@ void chol_lookahead(double* A, int n, int lda, CholWork& work, cudaStream_t st) 
             g.transB = true; g.alpha = -1.0; g.beta = 1.0; g.lower = 1;
             gemm(g, st);
         }
+        LRN_CUDA(cudaEventRecord(evR[p & 1], st));
+        // the next panel's columns on the panel stream (they also received rest(p-1), which must have completed)
+        if (p >= 1) LRN_CUDA(cudaStreamWaitEvent(sp, evR[(p - 1) & 1], 0));
+        gemm_nt(sp, n - q0, wq, w, -1.0, P, lda, P, lda, 1.0, A + (size_t)q0 * lda + q0, lda);
     }
+    LRN_CUDA(cudaStreamWaitEvent(st, evP[last], 0));
 }
 
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st) {

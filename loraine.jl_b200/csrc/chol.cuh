@@ -31,13 +31,6 @@ struct CholWork {
 // (inside diagonal 128-tiles it may be overwritten with don't-care values). Enqueues only; read `work.info` after a sync.
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st);
 
-// Factor one column panel: the w x w diagonal block at the top of `Apanel` (rows x w) and the TRSM of the rows below it.
-// `dinv` points at the 64x64 inverse blocks of this panel, `base` is the global index of its first column (for info).
-// If `Pout` is non-null the solved rows (below the diagonal block) are ALSO written to Pout + w (leading dimension ldp)
-// and the diagonal block is copied to Pout (packed panel for a broadcast).
-void cholesky_panel(double* Apanel, int rows, int w, int lda, double* dinv, int* info, int base, CholWork& work, double* Pout,
-                    int ldp, cudaStream_t st);
-
 // Factor ONE diagonal block (w <= 512) in place with a single launch; `dinv` receives its inverted 64 x 64 diagonal blocks and
 // X (w x w, leading dimension ldx, optional) the full inverse of the factor (lower triangular, zero above the diagonal).
 void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int ldx, int* info, int base, cudaStream_t st);
