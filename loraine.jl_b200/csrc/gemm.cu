@@ -256,7 +256,19 @@ __global__ void __launch_bounds__(288, 1) dgemm_dmma_bulk_kernel(const GemmParam
         // ---- producer warp: lane l moves k-line l of the A tile and of the B tile -----------------------------------
         const double* Ag = p.A + (size_t)z * p.sA + m0;
         const double* Bg = (TB ? p.B + n0 : p.B + (size_t)n0 * p.ldb) + (size_t)z * p.sB;
+        auto prefetch_c = [&]() {
+            // pull the 128 x 128 tile of C (read-modify-write epilogue, beta != 0) towards L2 while the main loop runs, so that
+            // the epilogue's reads do not wait on HBM: 128 columns x 8 lines of 128 B
+            const char* Cg = reinterpret_cast<const char*>(p.C + (size_t)z * p.sC + (size_t)n0 * p.ldc + m0);
+#pragma unroll 4
+            for (int col = lane; col < 128; col += 32) {
+                const char* cp = Cg + (size_t)col * p.ldc * sizeof(double);
+#pragma unroll
+                for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + q * 128));
+            }
+        };
         for (int kt = 0; kt < KT; kt++) {
+            if (p.beta != 0.0 && kt == (KT > STB ? STB : 0)) prefetch_c();   // after the pipeline is primed
             const int s = kt % STB;
             mbar_wait(bars + 8 * (STB + s), ((kt / STB) & 1) ^ 1);
             if (lane == 0) mbar_expect_tx(bars + 8 * s, 2u * BKB * 128u * 8u);

@@ -76,6 +76,29 @@ struct RowOwner {
     bool owns(int row) const { return world <= 1 || ((row / pw) % world) == rank; }
 };
 
+// ---- staged sparse-pair Schur assembly (pairs.cu) ------------------------------------------------------------------
+// Plan of the shared-memory staged pair kernel: constraints are taken in INDEX order in groups of up to 8 consecutive rows of
+// H whose distinct matrix indices (at most PAIR_MAXC per constraint) fit one CTA's shared memory as rows W[x, I] of the
+// symmetric scaling matrix; the column side streams the lower-triangle entry lists of all constraints k <= j, bucketed by
+// their entry count so that the lanes of a warp do the same amount of work.
+constexpr int PAIR_MAXC = 8;      // distinct indices per constraint matrix handled by the staged kernel
+constexpr int PAIR_ROWS = 8;      // rows of H per group (consecutive constraints: 64 B of a column of H per thread)
+struct PairPlan {
+    bool ok = false;
+    int ngroups = 0, nbuckets = 0, smax = 0;
+    size_t smem = 0;
+    // groups (descending row order = descending work): first row, rows, staged doubles per W row, offsets into gidx / rowA
+    DevBuf<int> g_r0, g_cnt, g_S, g_idx0;
+    DevBuf<int> gidx;              // per group: the S staged column indices of W (padding repeats a valid index)
+    DevBuf<int> row_off, row_c;    // per group row (ngroups * PAIR_ROWS): offset of its indices inside the staged row, count
+    DevBuf<double> rowA;           // per group row: dense symmetric PAIR_MAXC x PAIR_MAXC coefficient block (local indices)
+    // column side, bucket-major: members (constraint ids ascending inside a bucket), entry ranges, entries (p, q, weight)
+    DevBuf<int> b_first, b_ids, b_eptr;      // nbuckets + 1 ; members ; members + 1
+    std::vector<int> h_b_first;
+    DevBuf<int2> e_pq;
+    DevBuf<double> e_w;
+};
+
 // ---- sparse data of one PSD block --------------------------------------------------------------------------------
 struct SparseBlock {
     int m = 0, n_var = 0;
@@ -102,6 +125,7 @@ struct SparseBlock {
     DevBuf<int> part;
     int max_row_nnz = 0;
     bool all_single_diag = false;    // every participating matrix is v * e_a e_a^T
+    PairPlan pairs;                  // staged pair kernel (used when every matrix of the block goes through the F3 formula)
     // rank-one factors (datarank == -1): CSR n_var x m
     bool has_B = false;
     long long nnzB = 0;
@@ -133,6 +157,12 @@ void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int l
 //   H[max(j,k), min(j,k)] += tr(calA_j W calA_k W)
 void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh,
                     RowOwner own = RowOwner());
+// The same Schur term through the shared-memory staged kernel (pairs.cu); requires sb.pairs.ok.  All pairs of the block.
+void sp_schur_pairs_staged(cudaStream_t st, const SparseBlock& sb, const double* W, int ldw, double* H, int ldh,
+                           RowOwner own = RowOwner());
+// host: build sb.pairs from the by-constraint entry lists (0-based rowptr / p / q / value, symmetric storage required)
+void sp_build_pair_plan(SparseBlock& sb, const std::vector<int>& rowptr, const std::vector<int>& ep, const std::vector<int>& eq,
+                        const std::vector<double>& ev, cudaStream_t st);
 // F1 column (src/makeBBBB.jl:81-104): given U = W calA_j W dense, H[max(j,k),min(j,k)] += <calA_k, U> for positions kk >= jj
 void sp_schur_f1_column(cudaStream_t st, const SparseBlock& sb, int jj, const double* U, int ldu, double* H, int ldh,
                         RowOwner own = RowOwner());

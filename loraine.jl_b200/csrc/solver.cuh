@@ -108,6 +108,7 @@ struct lrn_solver {
     int rank = 0, world = 1;
     void* nccl = nullptr;              // lrn::DistCtx*
     int dist_pw = 512;                 // row block height of the block-cyclic Schur distribution
+    bool use_staged_pairs = true;      // sparse-pair Schur term through the shared-memory staged kernel when the block has a plan
     bool H_gathered = false;           // the row-block shards of H have already been summed over the ranks (parity hooks)
     void* group = nullptr;             // lrn::Group*: this handle is the facade of an in-process multi-GPU group (group.cuh)
 };
