@@ -77,12 +77,12 @@ struct RowOwner {
 };
 
 // ---- staged sparse-pair Schur assembly (pairs.cu) ------------------------------------------------------------------
-// Plan of the shared-memory staged pair kernel: constraints are taken in INDEX order in groups of up to 8 consecutive rows of
-// H whose distinct matrix indices (at most PAIR_MAXC per constraint) fit one CTA's shared memory as rows W[x, I] of the
-// symmetric scaling matrix; the column side streams the lower-triangle entry lists of all constraints k <= j, bucketed by
+// Plan of the shared-memory staged pair kernel: constraints are taken in INDEX order in groups of up to 8 consecutive COLUMNS
+// of H whose distinct matrix indices (at most PAIR_MAXC per constraint) fit one CTA's shared memory as rows W[x, I] of the
+// symmetric scaling matrix; the row side streams the lower-triangle entry lists of all constraints j >= k, bucketed by
 // their entry count so that the lanes of a warp do the same amount of work.
 constexpr int PAIR_MAXC = 8;      // distinct indices per constraint matrix handled by the staged kernel
-constexpr int PAIR_ROWS = 8;      // rows of H per group (consecutive constraints: 64 B of a column of H per thread)
+constexpr int PAIR_ROWS = 8;      // columns of H per group (consecutive constraints)
 struct PairPlan {
     bool ok = false;
     int ngroups = 0, nbuckets = 0, smax = 0;

@@ -1,13 +1,15 @@
 // Sparse-pair Schur assembly, F3 formula of makeBBBBsi (src/makeBBBB.jl:139-213, `_dot` :39-64), staged through shared memory:
 //     H[j,k] = tr(calA_j W calA_k W) = sum_{(p,q) in calA_k} v_k[p,q] T_j[p,q],      T_j = W calA_j W  sampled at k's entries,
 //     T_j[p,q] = W[p, I_j] A_j W[I_j, q]        (I_j = distinct indices of calA_j, A_j its |I_j| x |I_j| coefficient block).
-// A CTA owns up to 8 CONSECUTIVE constraints j (rows of H) and stages the rows W[x, I_j], x = 0..m-1, of all of them in shared
-// memory once ([x][S] layout: the |I_j| values a pair needs sit in one 16-byte aligned vector).  It then streams the
-// lower-triangle entry lists of every constraint k <= j (symmetric storage: T_j is symmetric, so the strict upper entries are
-// folded into doubled weights -- half the gathers of the reference loop), one thread per k; both gathers of an entry are two
-// vector loads from shared memory instead of 2 |calA_j| scalar gathers from L2.  The 8 results of a thread are 64 contiguous
-// bytes of column k of H.  Constraints k are bucketed by entry count (uniform work per warp) and sorted by index inside a
-// bucket (the k <= j restriction is a prefix).
+// (H is symmetric: the roles of j and k are interchangeable; the kernel stages on the COLUMN side.)
+// A CTA owns up to 8 CONSECUTIVE constraints k (columns of H) and stages the rows W[x, I_k], x = 0..m-1, of all of them in
+// shared memory once ([x][S] layout: the |I_k| values a pair needs sit in one 16-byte aligned vector).  It then streams the
+// lower-triangle entry lists of every constraint j >= k (symmetric storage: T_k is symmetric, so the strict upper entries are
+// folded into doubled weights -- half the gathers of the reference loop), one thread per j; both gathers of an entry are two
+// vector loads from shared memory instead of 2 |calA_k| scalar gathers from L2.  Consecutive threads handle consecutive rows j,
+// so the read-modify-write of a column of H is coalesced.  Constraints j are bucketed by entry count (uniform work per warp)
+// and sorted by index inside a bucket (the j >= k restriction is a suffix).  Multi-GPU: a thread skips the rows its rank does
+// not own (row blocks are runs of consecutive j, so warps stay uniform).
 // Bound: shared-memory bandwidth (random 16 B vector loads) -- algorithmic traffic 2 x 8 |I_j| bytes per (j, entry of k).
 #include "ops.cuh"
 #include <algorithm>
@@ -49,8 +51,7 @@ __global__ void __launch_bounds__(PT, 1)
     __shared__ double sA[PAIR_ROWS * PAIR_MAXC * PAIR_MAXC];
     __shared__ int s_off[PAIR_ROWS], s_c[PAIR_ROWS];
     const int g = blockIdx.x;
-    const int r0 = g_r0[g], cnt = g_cnt[g], S = g_S[g];
-    if (!own.owns(r0)) return;                       // groups never straddle a row block (aligned to 8 rows)
+    const int r0 = g_r0[g], cnt = g_cnt[g], S = g_S[g];      // columns r0 .. r0 + cnt - 1 of H
     const int tid = threadIdx.x;
     // ---- stage W[x, I] for the S indices of the group: Ws[x * S + ci] --------------------------------------------------
     {
@@ -63,22 +64,22 @@ __global__ void __launch_bounds__(PT, 1)
         if (tid < PAIR_ROWS) { s_off[tid] = row_off[g * PAIR_ROWS + tid]; s_c[tid] = row_c[g * PAIR_ROWS + tid]; }
     }
     __syncthreads();
-    const int jmax = r0 + cnt - 1;
     for (int b = 0; b < nbuckets; b++) {
         const int m0 = b_first[b], m1 = b_first[b + 1];
-        // members with id <= jmax: ids ascending inside the bucket -> binary search for the prefix length
+        // members with id >= r0: ids ascending inside the bucket -> binary search for the start of the suffix
         int lo = m0, hi = m1;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (b_ids[mid] <= jmax) lo = mid + 1; else hi = mid; }
-        for (int t = m0 + tid; t < lo; t += PT) {
-            const int k = b_ids[t];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (b_ids[mid] < r0) lo = mid + 1; else hi = mid; }
+        for (int t = lo + tid; t < m1; t += PT) {
+            const int j = b_ids[t];
+            if (!own.owns(j)) continue;
             const int f0 = b_eptr[t], f1 = b_eptr[t + 1];
-            double* dst = H + (size_t)k * ldh + r0;
+            double* dst = H + (size_t)r0 * ldh + j;
             // rows of the group one after the other (the branch on the size class is uniform over the CTA); the few entries
             // of k are re-read from L1 for every row
 #pragma unroll 1
             for (int r = 0; r < cnt; r++) {
                 const int c = s_c[r];
-                if (c == 0 || k > r0 + r) continue;            // no matrix in this block / above the diagonal of H
+                if (c == 0 || j < r0 + r) continue;            // no matrix in this block / above the diagonal of H
                 const int off = s_off[r];
                 const double* A = sA + r * PAIR_MAXC * PAIR_MAXC;
                 double acc = 0.0;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(PT, 1)
                         acc = fma(e_w[f], bilinear<8>(smem + (size_t)pq.x * S + off, smem + (size_t)pq.y * S + off, A), acc);
                     }
                 }
-                dst[r] += acc;
+                dst[(size_t)r * ldh] += acc;
             }
         }
     }
@@ -150,7 +151,7 @@ void sp_build_pair_plan(SparseBlock& sb, const std::vector<int>& rowptr, const s
             chunks.push_back({a, c});
         }
     }
-    std::sort(chunks.begin(), chunks.end(), [](auto& x, auto& y) { return x.first > y.first; });   // long rows first
+    std::sort(chunks.begin(), chunks.end(), [](auto& x, auto& y) { return x.first < y.first; });   // long columns first
     for (auto [a, c] : chunks) {
         int S = 0;
         bool any = false;

@@ -845,7 +845,8 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
                     sp_schur_f1_column(st, B.sp, jj, B.T3.p(), ld, h->H.p(), h->H.ld, own);
                 }
                 // F3 for the remaining (sparse) matrices                       (src/makeBBBB.jl:139-213)
-                if (B.sp.pairs.ok && h->use_staged_pairs) sp_schur_pairs_staged(st, B.sp, B.W.p(), ld, h->H.p(), h->H.ld, own);
+                if (B.sp.pairs.ok && (h->use_staged_pairs == 1 || (h->use_staged_pairs < 0 && B.sp.npart >= 1024)))
+                    sp_schur_pairs_staged(st, B.sp, B.W.p(), ld, h->H.p(), h->H.ld, own);
                 else sp_schur_pairs(st, B.sp, B.sp.nF1, B.W.p(), ld, h->H.p(), h->H.ld, own);
             }
         }
@@ -1320,7 +1321,7 @@ int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
         else if (n == "erank") { LRN_REQUIRE(h->prec_ready == 0, "erank cannot change after a preconditioner was built"); h->opt.erank = (int)value; }
         else if (n == "svd_tol") h->opt.svd_tol = value;
         else if (n == "lanczos_tol") h->opt.lanczos_tol = value;
-        else if (n == "pair_kernel") h->use_staged_pairs = (value != 0);   // 0: gather kernel (one thread per pair), 1: staged kernel
+        else if (n == "pair_kernel") h->use_staged_pairs = (int)value;   // 0: gather kernel (one thread per pair), 1: staged kernel, -1: auto
         else if (n == "sparse_op") {
             // 0: dense W M W operator, 1: sparse-aware operator wherever the data allows it, -1: automatic (density rule)
             for (auto& B : h->blk) {

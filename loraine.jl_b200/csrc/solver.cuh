@@ -108,7 +108,8 @@ struct lrn_solver {
     int rank = 0, world = 1;
     void* nccl = nullptr;              // lrn::DistCtx*
     int dist_pw = 512;                 // row block height of the block-cyclic Schur distribution
-    bool use_staged_pairs = true;      // sparse-pair Schur term through the shared-memory staged kernel when the block has a plan
+    int use_staged_pairs = -1;         // sparse-pair Schur term: 1 staged kernel (pairs.cu) when the block has a plan, 0 gather kernel,
+                                       // -1 automatic (staged from 1024 participating constraints per block on)
     bool H_gathered = false;           // the row-block shards of H have already been summed over the ranks (parity hooks)
     void* group = nullptr;             // lrn::Group*: this handle is the facade of an in-process multi-GPU group (group.cuh)
 };
