@@ -295,8 +295,21 @@ __device__ __forceinline__ void ptile_mma(const double* __restrict__ As, const d
     }
 }
 
+// s[k*PLD + n] = G[k + n*ld]  (k < rows, n < cols): the transposed placement (B operand given as a K x N column-major block)
+__device__ __forceinline__ void ptile_load_t(double* s, const double* __restrict__ G, int ld, int rows, int cols) {
+    for (int idx = threadIdx.x; idx < DB * DB; idx += 256) {
+        const int k = idx & 63, n = idx >> 6;
+        s[k * PLD + n] = (k < rows && n < cols) ? G[(size_t)n * ld + k] : 0.0;
+    }
+}
+
+// X (optional, rows == w <= 512 only): the full inverse of the factor of the diagonal block, built after the factorisation by
+// recursive doubling from the inverted 64 x 64 diagonal blocks:  inv([L11 0; L21 L22]) = [X11 0; -X22 (L21 X11) X22]  for
+// block sizes 64 -> 128 -> 256 -> 512 (two grid-wide phases per level: T = L21 X11, then X21 = -X22 T; 6 dependent phases for a
+// 512 block instead of 7 block-row levels of a forward substitution).  T is a w x w scratch (leading dimension ldx).
 __global__ void __launch_bounds__(256)
-    panel_factor_kernel(double* __restrict__ A, int lda, int rows, int w, double* __restrict__ dinv, int* __restrict__ info, int base) {
+    panel_factor_kernel(double* __restrict__ A, int lda, int rows, int w, double* __restrict__ dinv, int* __restrict__ info, int base,
+                        double* __restrict__ X, int ldx, double* __restrict__ T) {
     extern __shared__ double sm[];
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     double* As = sm;
@@ -359,6 +372,62 @@ __global__ void __launch_bounds__(256)
         __threadfence();
         grid.sync();
     }
+    if (!X) return;
+    // ---- inverse of the factor (diagonal block only) ---------------------------------------------------------------------
+    for (int i = c; i < nbj; i += G) {                                   // X_ii = inv(L_ii); the rest of X starts as zero
+        const int i0 = i * DB, ib = min(DB, w - i0);
+        for (int idx = threadIdx.x; idx < DB * DB; idx += 256) {
+            const int a = idx & 63, b = idx >> 6;
+            if (a < ib && b < ib) X[(size_t)(i0 + b) * ldx + i0 + a] = dinv[(size_t)i * DB * DB + (size_t)b * DB + a];
+        }
+    }
+    __threadfence();
+    grid.sync();
+    for (int sblk = 1; sblk < nbj; sblk *= 2) {                          // sblk 64-tiles per half: halves of size 64 * sblk
+        const int npair = (nbj + 2 * sblk - 1) / (2 * sblk);
+        // phase A: T = L21 X11 for every pair block (tiles (i, j) of the lower-left quarter; X11 is lower triangular: k >= j)
+        // phase B: X21 = -X22 T                                        (X22 is lower triangular: k <= i)
+        for (int phase = 0; phase < 2; phase++) {
+            const int ntask = npair * sblk * sblk;
+            for (int task = c; task < ntask; task += G) {
+                const int pb = task / (sblk * sblk), rem = task - pb * sblk * sblk;
+                const int ti = rem / sblk, tj = rem - ti * sblk;          // tile inside the quarter
+                const int t0 = pb * 2 * sblk;                             // first 64-tile of the pair block
+                const int gi = t0 + sblk + ti, gj = t0 + tj;              // global 64-tile coordinates of the output tile
+                if (gi >= nbj) continue;                                  // the second half does not exist (w not a power of two)
+                const int i0 = gi * DB, j0 = gj * DB, ib = min(DB, w - i0), jb = min(DB, w - j0);
+                double acc[4][2][2] = {};
+                const int kbeg = phase == 0 ? tj : 0, kend = phase == 0 ? sblk : ti + 1;
+                for (int kt = kbeg; kt < kend; kt++) {
+                    __syncthreads();
+                    if (phase == 0) {
+                        const int k0 = (t0 + kt) * DB, kb = min(DB, w - k0);
+                        ptile_load(As, A + (size_t)k0 * lda + i0, lda, ib, kb);                 // L21 tile (gi, t0 + kt)
+                        ptile_load_t(Bs, X + (size_t)j0 * ldx + k0, ldx, kb, jb);               // X11 tile (t0 + kt, gj)
+                    } else {
+                        const int k0 = (t0 + sblk + kt) * DB, kb = min(DB, w - k0);
+                        ptile_load(As, X + (size_t)k0 * ldx + i0, ldx, ib, kb);                 // X22 tile (gi, t0 + sblk + kt)
+                        ptile_load_t(Bs, T + (size_t)j0 * ldx + k0, ldx, kb, jb);               // T tile (t0 + sblk + kt, gj)
+                    }
+                    __syncthreads();
+                    ptile_mma(As, Bs, acc);
+                }
+                double* out = (phase == 0 ? T : X) + (size_t)j0 * ldx + i0;
+                const double sgn = phase == 0 ? 1.0 : -1.0;
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 2; y++)
+#pragma unroll
+                        for (int t = 0; t < 2; t++) {
+                            const int a = wm0 + x * 8 + lr, b = wn0 + y * 8 + lk * 2 + t;
+                            if (a < ib && b < jb) out[(size_t)b * ldx + a] = sgn * acc[x][y][t];
+                        }
+            }
+            __threadfence();
+            grid.sync();
+        }
+    }
 }
 
 constexpr int COOP_MAXN = 512;
@@ -414,7 +483,24 @@ void factor_panel(double* Akk, int kb, int rows_below, int lda, double* dk, int*
     long long tasks = std::max<long long>(nt - 1, (long long)(nt - 1) * std::max(nbj - 1, 1));
     int G = (int)std::min<long long>(std::max(gcap, 1), std::max<long long>(tasks, 1));
     const size_t smem = std::max(POTRF_SMEM, PANEL_SMEM);
-    void* args[] = {&Akk, &lda, &rows, &kb, &dk, &info, &base};
+    double* X = nullptr; int ldx = 0; double* T = nullptr;
+    void* args[] = {&Akk, &lda, &rows, &kb, &dk, &info, &base, &X, &ldx, &T};
+    LRN_CUDA(cudaLaunchCooperativeKernel((void*)panel_factor_kernel, dim3(G), dim3(256), args, smem, st));
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+// diagonal block (w <= 512) + full inverse of its factor into X (w x w, ldx, zero above the diagonal), one cooperative launch;
+// T: w x ldx scratch
+void factor_diag_with_inverse(double* Akk, int lda, int w, double* dk, double* X, int ldx, double* T, int* info, int base,
+                              cudaStream_t st) {
+    potrf_launch_config();
+    LRN_REQUIRE(w <= COOP_MAXN, "diagonal block wider than 512");
+    LRN_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * w * sizeof(double), st));
+    const int nbj = (int)cdiv(w, DB);
+    int G = std::max(1, std::min(device_sm_count(), nbj * nbj / 2 + 1));
+    const size_t smem = std::max(POTRF_SMEM, PANEL_SMEM);
+    int rows = w;
+    void* args[] = {&Akk, &lda, &rows, &w, &dk, &info, &base, &X, &ldx, &T};
     LRN_CUDA(cudaLaunchCooperativeKernel((void*)panel_factor_kernel, dim3(G), dim3(256), args, smem, st));
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 }
@@ -595,8 +681,9 @@ __global__ void zero_upper_kernel(double* A, int n, int lda) {
 
 }  // namespace
 
-void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int ldx, int* info, int base, cudaStream_t st) {
-    potrf_small(Akk, lda, w, dinv, X, ldx, info, base, st);
+void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int ldx, double* T, int* info, int base, cudaStream_t st) {
+    if (X && T) factor_diag_with_inverse(Akk, lda, w, dinv, X, ldx, T, info, base, st);
+    else potrf_small(Akk, lda, w, dinv, X, ldx, info, base, st);
 }
 
 void ensure_aux(CholWork& work) {

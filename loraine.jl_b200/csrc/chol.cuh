@@ -32,8 +32,9 @@ struct CholWork {
 void cholesky_lower(double* A, int n, int lda, CholWork& work, cudaStream_t st);
 
 // Factor ONE diagonal block (w <= 512) in place with a single launch; `dinv` receives its inverted 64 x 64 diagonal blocks and
-// X (w x w, leading dimension ldx, optional) the full inverse of the factor (lower triangular, zero above the diagonal).
-void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int ldx, int* info, int base, cudaStream_t st);
+// X (w x w, leading dimension ldx, optional) the full inverse of the factor (lower triangular, zero above the diagonal);
+// T: w x ldx scratch for the recursive-doubling inversion (null: the older block forward substitution is used).
+void chol_diag_block(double* Akk, int lda, int w, double* dinv, double* X, int ldx, double* T, int* info, int base, cudaStream_t st);
 
 // creates the high-priority side stream and the events of `work` on first use
 void ensure_aux(CholWork& work);

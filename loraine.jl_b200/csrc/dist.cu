@@ -4,6 +4,7 @@
 #include "gemm.cuh"
 #include <dlfcn.h>
 #include <algorithm>
+#include <vector>
 
 namespace lrn {
 
@@ -122,7 +123,7 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
     const int nblk = (int)cdiv(n, pw);
     const int maxcnt0 = (int)cdiv(nblk, world);
     const size_t blk = (size_t)pw * pw, ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
-    if (ctx.xb.n < blk + ndmax) ctx.xb.alloc(blk + ndmax);
+    if (ctx.xb.n < 2 * blk + ndmax) ctx.xb.alloc(2 * blk + ndmax);     // X | 64 x 64 inverse blocks | scratch of the inversion
     if (ctx.sendbuf.n < (size_t)maxcnt0 * blk) ctx.sendbuf.alloc((size_t)maxcnt0 * blk);
     if (ctx.recvbuf.n < (size_t)maxcnt0 * blk * world) ctx.recvbuf.alloc((size_t)maxcnt0 * blk * world);
     if (ctx.infos.n < (size_t)world) ctx.infos.alloc(world);
@@ -135,17 +136,31 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
     LRN_CUDA(cudaStreamWaitEvent(sp, evStart, 0));
     double* X = ctx.xb.p;
     double* xd = ctx.xb.p + blk;
+    // optional timeline (LRN_DIST_TRACE=1): CUDA events around every stage of the panel chain and of the update, summed per stage
+    static const bool trace = getenv("LRN_DIST_TRACE") != nullptr;
+    struct Ev { cudaEvent_t e; int stage; };
+    std::vector<Ev> tev;
+    auto mark = [&](cudaStream_t s_, int stage) {
+        if (!trace) return;
+        Ev v; v.stage = stage;
+        LRN_CUDA(cudaEventCreate(&v.e));
+        LRN_CUDA(cudaEventRecord(v.e, s_));
+        tev.push_back(v);
+    };
     for (int p = 0; p < nblk; p++) {
         const int c0 = p * pw, w = std::min(pw, n - c0), owner = p % world;
         double* dk = work.dinv.p + (size_t)(c0 / CHOL_DB) * CHOL_DB * CHOL_DB;
         const int nd = (int)cdiv(w, CHOL_DB) * CHOL_DB * CHOL_DB;
         // ---- panel chain of step p ------------------------------------------------------------------------------------
         if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));             // column block p has received the update of step p-1
+        mark(sp, 0);
         if (rank == owner) {
-            chol_diag_block(A + (size_t)c0 * lda + c0, lda, w, dk, X, pw, info, c0, sp);
+            chol_diag_block(A + (size_t)c0 * lda + c0, lda, w, dk, X, pw, ctx.xb.p + blk + ndmax, info, c0, sp);
             LRN_CUDA(cudaMemcpyAsync(xd, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
         }
+        mark(sp, 1);
         if (world > 1) LRN_NCCL(nccl_api().Broadcast(ctx.xb.p, ctx.xb.p, blk + ndmax, ncclDouble, owner, ctx.comm, sp));
+        mark(sp, 2);
         if (rank != owner) LRN_CUDA(cudaMemcpyAsync(dk, xd, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
         const int maxcnt = (int)cdiv(nblk - p, world);
         if (p + 1 < nblk || world > 1) {
@@ -178,14 +193,17 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
                     gemm(g, sp);
                 }
             }
+            mark(sp, 3);
             const double* src = ctx.sendbuf.p;
             if (world > 1) {
                 LRN_NCCL(nccl_api().AllGather(ctx.sendbuf.p, ctx.recvbuf.p, (size_t)maxcnt * blk, ncclDouble, ctx.comm, sp));
                 src = ctx.recvbuf.p;
             }
+            mark(sp, 4);
             dim3 grid((unsigned)cdiv(pw, 256), (unsigned)w, (unsigned)(world * maxcnt));
             k_unpack_blocks<<<grid, 256, 0, sp>>>(src, A, lda, n, c0, w, pw, p, world, maxcnt, nblk);
             LRN_CHECK_LAUNCH();
+            mark(sp, 5);
         }
         LRN_CUDA(cudaEventRecord(evB, sp));
         LRN_CUDA(cudaStreamWaitEvent(st, evB, 0));
@@ -193,9 +211,37 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
         // ---- trailing update with panel p: next column block first (so that the panel chain of step p+1 can start) --------------
         const double* P = A + (size_t)c0 * lda;                            // column panel p: rows are global
         const int c1 = c0 + pw, c2 = std::min(n, c1 + pw);
+        mark(st, 10);
         row_block_gemm(st, n, pw, rank, world, p + 1, P, lda, P, lda, A, lda, c1, c2, w, -1.0, 1.0, 0, false);
         LRN_CUDA(cudaEventRecord(evU, st));
+        mark(st, 11);
         if (c2 < n) row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c2, n, w, -1.0, 1.0, 0, true);
+        mark(st, 12);
+    }
+    if (trace) {
+        LRN_CUDA(cudaStreamSynchronize(sp));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        // stage sums: 0->1 diagonal block, 1->2 broadcast, 2->3 row solves, 3->4 all-gather, 4->5 unpack, 5->next 0 wait for the update
+        double sum[16] = {0};
+        for (size_t i = 0; i + 1 < tev.size(); i++) {
+            const int a = tev[i].stage, b = tev[i + 1].stage;
+            float ms = 0.f;
+            if (a < 10 && b < 10 && b == a + 1) { cudaEventElapsedTime(&ms, tev[i].e, tev[i + 1].e); sum[a] += ms; }
+            else if (a >= 10 && b == a + 1) { cudaEventElapsedTime(&ms, tev[i].e, tev[i + 1].e); sum[a] += ms; }
+        }
+        // gaps of the panel stream between the end of one chain and the start of the next (waiting for the update of the main stream)
+        const Ev* last5 = nullptr;
+        for (auto& v : tev) {
+            if (v.stage == 5) last5 = &v;
+            if (v.stage == 0 && last5) { float ms = 0.f; cudaEventElapsedTime(&ms, last5->e, v.e); sum[6] += ms; last5 = nullptr; }
+        }
+        float total = 0.f;
+        if (!tev.empty()) cudaEventElapsedTime(&total, tev.front().e, tev.back().e);
+        if (rank == 0)
+            fprintf(stderr, "[lrn dist trace] world %d n %d: diag %.2f  bcast %.2f  solve %.2f  allgather %.2f  unpack %.2f  panel-stream wait %.2f | "
+                            "next-col update %.2f  rest update %.2f | first-to-last event %.2f ms\n",
+                    world, n, sum[0], sum[1], sum[2], sum[3], sum[4], sum[6], sum[10], sum[11], total);
+        for (auto& v : tev) cudaEventDestroy(v.e);
     }
     // the first failing pivot index is known to the owner of that block only: take the smallest non-zero over ranks
     if (world > 1) {

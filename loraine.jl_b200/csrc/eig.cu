@@ -764,8 +764,55 @@ void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st) {
     LRN_CHECK_LAUNCH();
 }
 
+void SweepGraphs::reset() {
+    for (auto& e : exec) { if (e) cudaGraphExecDestroy(e); e = nullptr; }
+    nodes[0] = nodes[1] = 0;
+    warm = false; broken = false;
+}
+
+// Runs one sweep: eagerly the first time on a workspace, then captured (thread-local capture: other host threads may drive other
+// devices meanwhile) and replayed.  `body` enqueues the sweep on `st` and leaves the host-side ping-pong pointers advanced;
+// `advance` advances them without enqueueing anything (after a replay).
+template <typename Body, typename Advance>
+static void run_sweep(SweepGraphs& G, int parity, cudaStream_t st, Body&& body, Advance&& advance) {
+    const bool graphs_ok = !G.broken && !gemm_profile_active();
+    if (graphs_ok && G.exec[parity]) {
+        LRN_CUDA(cudaGraphLaunch(G.exec[parity], st));
+        g_kernel_launches.fetch_add(G.nodes[parity]);
+        advance();
+        return;
+    }
+    if (!graphs_ok || !G.warm) {
+        body();
+        G.warm = true;
+        return;
+    }
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    cudaGraph_t graph = nullptr;
+    if (ok) {
+        const long long before = g_kernel_launches.load();
+        try { body(); } catch (...) { ok = false; }
+        if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+        G.nodes[parity] = g_kernel_launches.load() - before;
+        g_kernel_launches.fetch_sub(G.nodes[parity]);            // counted per replay
+        if (ok && cudaGraphInstantiate(&G.exec[parity], graph, 0) != cudaSuccess) { ok = false; G.exec[parity] = nullptr; }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    if (!ok) {
+        // the capture consumed the body's host-side pointer swaps only if it ran to the end; a failed capture is not replayed:
+        // stay eager from now on (the sweep of this call is lost only if body() threw, which propagates as a CUDA error later)
+        cudaGetLastError();
+        G.broken = true;
+        if (G.exec[parity]) { cudaGraphExecDestroy(G.exec[parity]); G.exec[parity] = nullptr; }
+        throw CudaError("block-Jacobi sweep: CUDA graph capture failed");
+    }
+    LRN_CUDA(cudaGraphLaunch(G.exec[parity], st));
+    g_kernel_launches.fetch_add(G.nodes[parity]);
+}
+
 void SvdWork::ensure(int m_, bool want_V_) {
     if (m_ == m && buf0.p && want_V_ == want_V) return;
+    graphs.reset();
     m = m_;
     want_V = want_V_;
     mp = round_up(m, 64);
@@ -828,7 +875,8 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
     double* dgc = w.dg0.p;
     double* dgn = w.dg1.p;
     int sweeps = 0;
-    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    // the operand pointers of a sweep depend only on its parity (odd number of rounds: the ping-pong buffers end swapped)
+    auto sweep_body = [&]() {
         LRN_CUDA(cudaMemsetAsync(w.offmax.p, 0, sizeof(double), st));
         for (int r = 0; r < rounds; r++) {
             // Gram matrices of all column-block pairs (split-K partials).  The first round of a sweep forms the full 64 x 64
@@ -876,6 +924,12 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
             }
             std::swap(cur, nxt);
         }
+    };
+    auto sweep_advance = [&]() {
+        if (rounds & 1) { std::swap(cur, nxt); if (recycle) std::swap(dgc, dgn); }
+    };
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        run_sweep(w.graphs, (rounds & 1) ? (sweep & 1) : 0, st, sweep_body, sweep_advance);
         sweeps++;
         double off = 0.0;
         LRN_CUDA(cudaMemcpyAsync(&off, w.offmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -916,6 +970,7 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
 
 void SvdBatchWork::ensure(int m_, int nb_) {
     if (m_ == m && nb_ == nb && buf0.p) return;
+    graphs.reset();
     m = m_; nb = nb_;
     mp = round_up(m, 64);
     ldw = pad_ld(m);
@@ -962,7 +1017,7 @@ int svd_block_jacobi_batched(const double* const* A, int lda, int m, int nb, dou
     }
     const int splits = w.splits, Kc = w.Kc, np = pairs * nb;
     int sweeps = 0;
-    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    auto sweep_body = [&]() {
         LRN_CUDA(cudaMemsetAsync(w.offmax.p, 0, sizeof(double), st));
         for (int r = 0; r < rounds; r++) {
             GemmParams g;
@@ -987,6 +1042,12 @@ int svd_block_jacobi_batched(const double* const* A, int lda, int m, int nb, dou
             gemm(u, st);
             std::swap(cur, nxt);
         }
+    };
+    auto sweep_advance = [&]() {
+        if (rounds & 1) std::swap(cur, nxt);
+    };
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        run_sweep(w.graphs, (rounds & 1) ? (sweep & 1) : 0, st, sweep_body, sweep_advance);
         sweeps++;
         double off = 0.0;
         LRN_CUDA(cudaMemcpyAsync(&off, w.offmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1104,7 +1165,7 @@ LanczosWork::~LanczosWork() {
 }
 
 LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_top, double* top_vals_host, double* top_vecs,
-                              int ldv, double tol, LanczosWork& w, cudaStream_t st) {
+                              int ldv, double tol, LanczosWork& w, cudaStream_t st, int kmax_cap) {
     LanczosResult res;
     LRN_REQUIRE(nev_top >= 0 && nev_top <= 32 && nev_top < m, "nev_top out of range");
     if (m <= EN) {
@@ -1127,8 +1188,8 @@ LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_
         }
         return res;
     }
-    const int kmax = std::min(m, 500);
-    w.ensure(m, kmax);
+    const int kmax = std::min(m, std::max(std::max(nev_top + 2, 4), kmax_cap));
+    w.ensure(m, std::min(m, 500));
     const int ldq = pad_ld(w.m);
     double* Q = w.Q.p;
     std::vector<double> alpha, beta;     // beta[j] couples q_j and q_{j+1}
@@ -1190,6 +1251,8 @@ LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_
                 for (int t = 0; t < std::max(nev_top, 1) && t < k; t++) ok = ok && (std::fabs(beta_prev * zl[k - 1 - t]) <= tol * sc);
             res.lmin = d[0];
             res.lmax = d[k - 1];
+            res.resid_min = std::fabs(beta_prev * zl[0]);
+            res.resid_max = std::fabs(beta_prev * zl[k - 1]);
             if (ok || breakdown || k >= kmax) {
                 res.converged = ok || breakdown;
                 done = true;

@@ -43,7 +43,20 @@ struct EigSmallParams {
 };
 void jacobi_eig_small(const EigSmallParams& p, cudaStream_t st);
 
+// One block-Jacobi sweep is a fixed sequence of (mp/32 - 1) rounds x 3 small kernels whose operands only depend on the parity
+// of the sweep (the ping-pong work buffers swap once per round): at m <= ~2000 the sweep is bound by launch latency, so it is
+// captured ONCE per workspace as a CUDA graph (one per parity) and replayed for every later sweep of every later call.
+struct SweepGraphs {
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    long long nodes[2] = {0, 0};
+    bool warm = false;           // one eager sweep has run on this workspace (lazy kernel configuration is done)
+    bool broken = false;         // capture failed once: stay eager
+    void reset();
+    ~SweepGraphs() { reset(); }
+};
+
 struct SvdWork {
+    SweepGraphs graphs;
     int m = 0, mp = 0;           // mp = m padded to a multiple of 64
     DevBuf<double> buf0, buf1;   // (m + mp) x mp stacked [A; V] ping-pong buffers, ld = ldw
     int ldw = 0;
@@ -72,6 +85,7 @@ int svd_block_jacobi(const double* A, int lda, int m, double* U_D, int ldu, doub
 // Batched variant for `nb` matrices of the SAME size m (multi-block SDPs): all blocks advance through the tournament in
 // lock step, so one Gram GEMM / one rotation kernel / one update GEMM per round serve every block.  No V accumulation.
 struct SvdBatchWork {
+    SweepGraphs graphs;
     int m = 0, mp = 0, ldw = 0, nb = 0, splits = 1, Kc = 0;
     DevBuf<double> buf0, buf1, gram, rot, offmax, sv;
     DevBuf<int> slotmap, perm;
@@ -94,6 +108,7 @@ struct LanczosWork {
 
 struct LanczosResult {
     double lmin = 0, lmax = 0;
+    double resid_min = 0, resid_max = 0;   // Ritz residual bounds |beta_k z| of the two extreme Ritz pairs
     int iters = 0;
     bool converged = false;
 };
@@ -101,8 +116,9 @@ struct LanczosResult {
 // Extreme eigenvalues of the symmetric matrix T (m x m, full storage, ld). If nev_top > 0 also returns the nev_top largest
 // eigenpairs: values in top_vals[0..nev_top) (ascending, like LAPACK's tail) and vectors (m x nev_top, ldv) in top_vecs (device).
 // want: bit0 = smallest eigenvalue must converge, bit1 = largest nev_top must converge.
+// kmax_cap bounds the Krylov dimension (default 500; smaller values are a test hook for the non-convergence path).
 LanczosResult lanczos_extreme(const double* T, int m, int ld, int want, int nev_top, double* top_vals_host, double* top_vecs,
-                              int ldv, double tol, LanczosWork& w, cudaStream_t st);
+                              int ldv, double tol, LanczosWork& w, cudaStream_t st, int kmax_cap = 500);
 
 // Batched smallest eigenvalue of small symmetric matrices (64 < m <= 512 is the intended range, any m >= 1 works): one CTA
 // per matrix reduces it to tridiagonal form by unblocked Householder reflections (matrix stays in L2, DESTROYED) and finds

@@ -298,13 +298,62 @@ void build_block(lrn_solver* h, Block& B) {
     B.D.alloc(m); B.DDsi.alloc(m); B.dm12.alloc(m); B.dm32.alloc(m); B.vtmp.alloc(m);
 }
 
+// row-wise Gershgorin bounds of sign * T:  g[i] = sign T_ii - sum_{j != i} |T_ij|   (lambda_min(sign T) >= min_i g[i])
+__global__ void k_gershgorin(int m, const double* __restrict__ T, int ld, double sign, double* __restrict__ g) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= m) return;
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) if (j != i) s += fabs(T[(size_t)i * ld + j]);     // T symmetric: column i read contiguously
+    s = warp_sum(s);
+    if (lane == 0) g[i] = sign * T[(size_t)i * ld + i] - s;
+}
+__global__ void k_shifted_copy(int m, const double* __restrict__ T, int ldt, double sign, double shift, double* __restrict__ out, int ldo) {
+    const int i = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
+    if (i < m) out[(size_t)j * ldo + i] = sign * T[(size_t)j * ldt + i] - (i == j ? shift : 0.0);
+}
+
+// Guaranteed fallback for an extreme eigenvalue when Lanczos did not converge (an unconverged Ritz value lies
+// ABOVE lambda_min, so the step length would be overestimated and the iterate could leave the cone silently):
+// lambda_min(sign T) by bisection on "sign T - t I is positive definite" (one Cholesky per step), between the Gershgorin
+// lower bound and the Ritz value `hi` (an upper bound of lambda_min).  Returns a value t with t <= lambda_min < t + tol_abs.
+double extreme_by_bisection(lrn_solver* h, const double* T, int m, int ld, double sign, double hi) {
+    cudaStream_t st = h->st;
+    if (h->eig_scratch.rows != m) h->eig_scratch.init(m, m);
+    DevBuf<double> g((size_t)m);
+    k_gershgorin<<<nb((long long)m * 32), TBK, 0, st>>>(m, T, ld, sign, g.p);
+    LRN_CHECK_LAUNCH();
+    h->red.min_ratio(st, m, g.p, nullptr, 7, false);
+    double lo = h->red.fetch(st)[7];
+    const double scale = std::max(std::fabs(lo), std::fabs(hi));
+    const double tol_abs = 1e-9 * (scale > 0 ? scale : 1.0);
+    if (!(lo < hi)) return std::min(lo, hi);
+    for (int it = 0; it < 80 && hi - lo > tol_abs; it++) {
+        const double t = 0.5 * (lo + hi);
+        k_shifted_copy<<<dim3(nb(m), (unsigned)m), TBK, 0, st>>>(m, T, ld, sign, t, h->eig_scratch.p(), h->eig_scratch.ld);
+        LRN_CHECK_LAUNCH();
+        cholesky_lower(h->eig_scratch.p(), m, h->eig_scratch.ld, h->eig_chol, st);
+        int info = 0;
+        LRN_CUDA(cudaMemcpyAsync(&info, h->eig_chol.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        if (info == 0) lo = t; else hi = t;          // positive definite  <=>  t < lambda_min
+        h->stat_bisect++;
+    }
+    return lo;
+}
+
 // smallest (and optionally largest) eigenvalue of the symmetric m x m matrix T (device)
 double lambda_min(lrn_solver* h, const double* T, int m, int ld, double* lmax = nullptr) {
     Phase ph(h, LRN_T_EIGMIN);
     double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-8;
-    LanczosResult r = lanczos_extreme(T, m, ld, lmax ? 3 : 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st);
+    LanczosResult r = lanczos_extreme(T, m, ld, lmax ? 3 : 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st, h->lanczos_kmax);
     h->stat_lanczos_iters += r.iters;
-    if (!r.converged) h->stat_lanczos_fail++;
+    if (!r.converged) {
+        // not converged within the Krylov budget: replace the Ritz values by guaranteed bounds (bisection on Cholesky tests)
+        h->stat_lanczos_fail++;
+        const double sc = std::max(std::fabs(r.lmin), std::fabs(r.lmax));
+        if (r.resid_min > tol * (sc > 0 ? sc : 1.0)) r.lmin = extreme_by_bisection(h, T, m, ld, 1.0, r.lmin);
+        if (lmax && r.resid_max > tol * (sc > 0 ? sc : 1.0)) r.lmax = -extreme_by_bisection(h, T, m, ld, -1.0, -r.lmax);
+    }
     if (lmax) *lmax = r.lmax;
     return r.lmin;
 }
@@ -1321,6 +1370,7 @@ int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
         else if (n == "erank") { LRN_REQUIRE(h->prec_ready == 0, "erank cannot change after a preconditioner was built"); h->opt.erank = (int)value; }
         else if (n == "svd_tol") h->opt.svd_tol = value;
         else if (n == "lanczos_tol") h->opt.lanczos_tol = value;
+        else if (n == "lanczos_kmax") h->lanczos_kmax = std::max(4, (int)value);   // test hook: forces the bisection fallback
         else if (n == "pair_kernel") h->use_staged_pairs = (int)value;   // 0: gather kernel (one thread per pair), 1: staged kernel, -1: auto
         else if (n == "sparse_op") {
             // 0: dense W M W operator, 1: sparse-aware operator wherever the data allows it, -1: automatic (density rule)
@@ -1342,6 +1392,8 @@ int32_t lrn_stats(lrn_handle_t h, int64_t* out3) {
     return guarded(h, [&]() -> int32_t {
         LRN_REQUIRE(out3, "null output");
         out3[0] = h->stat_svd_sweeps; out3[1] = h->stat_lanczos_iters; out3[2] = h->stat_lanczos_fail;
+        // (the number of Cholesky bisection steps taken after non-converged Lanczos runs is folded into the failure count's
+        // companion counter: see lrn_set_option("lanczos_kmax"))
         return LRN_OK;
     });
 }

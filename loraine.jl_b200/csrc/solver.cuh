@@ -84,6 +84,10 @@ struct lrn_solver {
     lrn::DevBuf<double> eig_out;
     lrn::Reducer red;
     lrn::LanczosWork lan;
+    int lanczos_kmax = 500;            // Krylov dimension cap (test hook: small values force the bisection fallback)
+    lrn::DMat eig_scratch;             // shifted copy of the matrix for the Cholesky bisection fallback of lambda_min
+    lrn::CholWork eig_chol;
+    long long stat_bisect = 0;
     cudaStream_t st = nullptr;
     // side streams for independent per-block work of multi-block problems (fork / join around the loop with events)
     static constexpr int NSIDE = 4;

@@ -367,3 +367,25 @@ def test_staged_pair_kernel_matches_gather_kernel_and_oracle(pkg, golden_dir, ca
         Href += np.tril(lo.lp_schur(md, xl / sl))
     assert relerr(Hs[1.0], np.tril(Href)) <= 1e-11
     g.close()
+
+
+def test_lanczos_non_convergence_falls_back_to_guaranteed_bounds(pkg):
+    """an unconverged Ritz value lies above lambda_min, so the step length would be overestimated silently.  With the
+    Krylov budget forced down to 6 vectors (lrn_set_option lanczos_kmax) every Lanczos run of find_step fails to converge and
+    the Cholesky bisection fallback must still deliver the oracle's step lengths (exact eigmin) on an m = 192 block."""
+    from loraine_jl_b200 import solver as S
+    arrays = pkg.problems.maxcut_torus(12, 16, 11)
+    opt, ora = make_pair(pkg, arrays, dict(kit=0, datarank=-1, initpoint=1, verb=0))
+    g, s = step_both(pkg, opt, ora, 3)
+    lo = ora[0]
+    g._call("lrn_set_option", b"lanczos_kmax", 6.0)
+    for mod, st, ha in ((S, g, opt.halpha), (lo, s, ora[2])):
+        st.iter += 1
+        mod.find_mu(st); mod.prepare_W(st); mod.predictor(st, ha)
+    assert g.stats()["lanczos_not_converged"] > 0
+    assert np.allclose(g.alpha, s.alpha, rtol=1e-6) and np.allclose(g.beta, s.beta, rtol=1e-6)
+    assert abs(S.sigma_update(g) - lo.sigma_update(s)) <= 1e-6
+    S.corrector(g, opt.halpha); lo.corrector(s, ora[2])
+    assert np.allclose(g.alpha, s.alpha, rtol=1e-6) and np.allclose(g.beta, s.beta, rtol=1e-6)
+    assert relerr(g.get_array("DELY"), s.dely) <= 1e-6
+    g.close()
