@@ -787,24 +787,32 @@ static void run_sweep(SweepGraphs& G, int parity, cudaStream_t st, Body&& body, 
         G.warm = true;
         return;
     }
-    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    cudaGraph_t graph = nullptr;
-    if (ok) {
-        const long long before = g_kernel_launches.load();
-        try { body(); } catch (...) { ok = false; }
-        if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
-        G.nodes[parity] = g_kernel_launches.load() - before;
-        g_kernel_launches.fetch_sub(G.nodes[parity]);            // counted per replay
-        if (ok && cudaGraphInstantiate(&G.exec[parity], graph, 0) != cudaSuccess) { ok = false; G.exec[parity] = nullptr; }
-        if (graph) cudaGraphDestroy(graph);
-    }
+    // (the legacy default stream cannot be captured: callers that run on it, like the debug hooks, stay eager)
+    bool ok = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+              cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (!ok) {
-        // the capture consumed the body's host-side pointer swaps only if it ran to the end; a failed capture is not replayed:
-        // stay eager from now on (the sweep of this call is lost only if body() threw, which propagates as a CUDA error later)
         cudaGetLastError();
         G.broken = true;
-        if (G.exec[parity]) { cudaGraphExecDestroy(G.exec[parity]); G.exec[parity] = nullptr; }
-        throw CudaError("block-Jacobi sweep: CUDA graph capture failed");
+        body();
+        return;
+    }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_kernel_launches.load();
+    try { body(); } catch (...) { ok = false; }
+    if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+    G.nodes[parity] = g_kernel_launches.load() - before;
+    g_kernel_launches.fetch_sub(G.nodes[parity]);            // counted per replay
+    if (ok && cudaGraphInstantiate(&G.exec[parity], graph, 0) != cudaSuccess) { ok = false; G.exec[parity] = nullptr; }
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        // nothing was enqueued by the captured body, but it advanced the host-side ping-pong pointers: put them back (the
+        // advance is its own inverse) and run the sweep eagerly; stay eager from now on
+        cudaGetLastError();
+        G.broken = true;
+        G.nodes[parity] = 0;
+        advance();
+        body();
+        return;
     }
     LRN_CUDA(cudaGraphLaunch(G.exec[parity], st));
     g_kernel_launches.fetch_add(G.nodes[parity]);

@@ -372,9 +372,10 @@ def test_staged_pair_kernel_matches_gather_kernel_and_oracle(pkg, golden_dir, ca
 def test_lanczos_non_convergence_falls_back_to_guaranteed_bounds(pkg):
     """an unconverged Ritz value lies above lambda_min, so the step length would be overestimated silently.  With the
     Krylov budget forced down to 6 vectors (lrn_set_option lanczos_kmax) every Lanczos run of find_step fails to converge and
-    the Cholesky bisection fallback must still deliver the oracle's step lengths (exact eigmin) on an m = 192 block."""
+    the Cholesky bisection fallback must still deliver the oracle's step lengths (exact eigmin) on an m = 480 block (blocks
+    up to 384 use the tridiagonalisation kernel instead of Lanczos)."""
     from loraine_jl_b200 import solver as S
-    arrays = pkg.problems.maxcut_torus(12, 16, 11)
+    arrays = pkg.problems.maxcut_torus(20, 24, 11)
     opt, ora = make_pair(pkg, arrays, dict(kit=0, datarank=-1, initpoint=1, verb=0))
     g, s = step_both(pkg, opt, ora, 3)
     lo = ora[0]
