@@ -318,11 +318,13 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16, lr = lane >> 2, lk = lane & 3;
     const int nbj = (w + DB - 1) / DB, nt = (rows + DB - 1) / DB;
+    // The 64 x 64 diagonal block of step j + 1 is factored by CTA 0 DURING the update phase of step j (right after it has applied
+    // step j to that block), so a step costs two grid barriers and the register factorisation hides behind the tile updates.
+    if (c == 0) potrf64_block(A, lda, min(DB, w), dinv, info, base, sm);
+    __threadfence();
+    grid.sync();
     for (int j = 0; j < nbj; j++) {
         const int j0 = j * DB, jb = min(DB, w - j0);
-        if (c == 0) potrf64_block(A + (size_t)j0 * lda + j0, lda, jb, dinv + (size_t)j * DB * DB, info, base + j0, sm);
-        __threadfence();
-        grid.sync();
         // ---- row tiles below the diagonal block of this step: P_i <- A_ij inv(L_jj)^T -------------------------------
         for (int i = j + 1 + c; i < nt; i += G) {
             const int i0 = i * DB, ib = min(DB, rows - i0);
@@ -348,7 +350,10 @@ __global__ void __launch_bounds__(256)
         const int nk = nbj - 1 - j;
         if (nk > 0) {
             const long long ntask = (long long)(nt - 1 - j) * nk;
-            for (long long task = c; task < ntask; task += G) {
+            // task 0 is the next diagonal tile (j+1, j+1): CTA 0 takes it, factors that tile, and (only when it is alone) the rest;
+            // the other CTAs share tasks 1 .. ntask-1
+            const long long tfirst = (c == 0) ? 0 : c, tstride = (G > 1) ? (c == 0 ? ntask : G - 1) : 1;
+            for (long long task = tfirst; task < ntask; task += tstride) {
                 const int i = j + 1 + (int)(task / nk), k = j + 1 + (int)(task % nk);
                 if (k > i) continue;                                   // block-uniform: above the diagonal of the panel
                 const int i0 = i * DB, k0 = k * DB, ib = min(DB, rows - i0), kb = min(DB, w - k0);
@@ -367,10 +372,16 @@ __global__ void __launch_bounds__(256)
                             const int a = wm0 + x * 8 + lr, b = wn0 + y * 8 + lk * 2 + t;
                             if (a < ib && b < kb) A[(size_t)(k0 + b) * lda + i0 + a] -= acc[x][y][t];
                         }
+                if (task == 0) {                                       // (CTA 0 only) the next diagonal tile is final: factor it now
+                    const int n0 = (j + 1) * DB;
+                    __threadfence_block();
+                    __syncthreads();
+                    potrf64_block(A + (size_t)n0 * lda + n0, lda, min(DB, w - n0), dinv + (size_t)(j + 1) * DB * DB, info, base + n0, sm);
+                }
             }
+            __threadfence();
+            grid.sync();
         }
-        __threadfence();
-        grid.sync();
     }
     if (!X) return;
     // ---- inverse of the factor (diagonal block only) ---------------------------------------------------------------------

@@ -5,6 +5,8 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <vector>
+#include <unistd.h>
+#include <mutex>
 
 namespace lrn {
 
@@ -35,6 +37,8 @@ const NcclApi& nccl_api() {
 }
 
 DistCtx::~DistCtx() {
+    for (void* m : ipc_opened) cudaIpcCloseMemHandle(m);
+    ipc_opened.clear();
     if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
     comm = nullptr;
 }
@@ -61,6 +65,185 @@ __global__ void k_min_nonzero(int* a, const int* b, int cnt) {
 __global__ void k_copy_block(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i < rows && j < cols) dst[(size_t)j * ldd + i] = src[(size_t)j * lds + i];
+}
+
+// ---- peer-memory exchange kernels ------------------------------------------------------------------------------------------
+constexpr long long P2P_SPIN_LIMIT = 4000000000LL;     // ~2 s of SM clocks: a lost peer must not hang the GPU
+
+// copy `count` doubles (multiple of 2) from src to the same offset of every peer buffer, then publish `stamp` in every peer's
+// flag word `slot` (the last CTA to finish does it, after a system-wide fence)
+__global__ void k_push_vec(const double* src, double* const* __restrict__ peers, int world, int self, size_t count,
+                           int* const* __restrict__ peer_flags, int slot, int stamp, unsigned int* __restrict__ done_ctr) {
+    const size_t n2 = count / 2;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 v = s2[i];
+        for (int r = 0; r < world; r++)
+            if (r != self) reinterpret_cast<double2*>(peers[r])[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_ctr, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_ctr = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; r++) *reinterpret_cast<volatile int*>(peer_flags[r] + slot) = stamp;
+        }
+    }
+}
+// my solved row blocks of panel p (send[z], pw x w, ld pw; block g = first + z * world) -> every peer's L at their final place
+__global__ void k_push_blocks(const double* __restrict__ send, double* const* __restrict__ peers, int world, int lda, int n, int c0,
+                              int w, int pw, int first, int cnt, int* const* __restrict__ peer_flags, int slot, int stamp,
+                              unsigned int* __restrict__ done_ctr) {
+    // grid: (row pairs of a block, column, slot z)
+    const int z = blockIdx.z, j = blockIdx.y;
+    const int g = first + z * world;
+    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int row = g * pw + i;
+    if (z < cnt && j < w && i < pw && row < n) {
+        const double* sp_ = send + ((size_t)z * pw + j) * pw + i;
+        const size_t off = (size_t)(c0 + j) * lda + row;
+        if (row + 1 < n && i + 1 < pw) {
+            const double2 v = *reinterpret_cast<const double2*>(sp_);
+            for (int r = 0; r < world; r++) *reinterpret_cast<double2*>(peers[r] + off) = v;
+        } else {
+            const double v = *sp_;
+            for (int r = 0; r < world; r++) peers[r][off] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned int prev = atomicAdd(done_ctr, 1u);
+        if (prev == total - 1) {
+            *done_ctr = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; r++) *reinterpret_cast<volatile int*>(peer_flags[r] + slot) = stamp;
+        }
+    }
+}
+// wait until flags[slot0 .. slot0 + nslots) have all reached `stamp` (written by the peers over NVLink)
+__global__ void k_wait_flags(volatile int* flags, int slot0, int nslots, int stamp) {
+    const int t = threadIdx.x;
+    if (t < nslots) {
+        const long long t0 = clock64();
+        while (flags[slot0 + t] < stamp) {
+            if (clock64() - t0 > P2P_SPIN_LIMIT) { flags[63] = 1; break; }
+        }
+    }
+    __threadfence_system();
+}
+
+__global__ void k_check_timeout(int* flags, int* info) {
+    if (flags[63] != 0) { *info = -77; flags[63] = 0; }
+}
+
+struct IpcPacket {
+    cudaIpcMemHandle_t hx, hl;
+    unsigned long long px, pl;          // raw pointers (same-process peers)
+    unsigned long long ox, ol;          // byte offsets of the buffers inside their underlying allocations (IPC maps the base)
+    long long pid;
+    int dev, pad;
+};
+
+// offset of a device pointer inside the allocation cudaIpcGetMemHandle exports (cuMemGetAddressRange, resolved at run time)
+size_t alloc_offset(const void* ptr) {
+    typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+    static fn_t fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* hnd = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (hnd) fn = (fn_t)dlsym(hnd, "cuMemGetAddressRange_v2");
+    });
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn && fn(&base, &size, (unsigned long long)ptr) == 0 && base) return (size_t)((unsigned long long)ptr - base);
+    return 0;
+}
+
+// One-time (per factor matrix) exchange of the buffer mappings.  Collective.  Leaves ctx.p2p = 1 on success on ALL ranks,
+// 0 otherwise (agreed with a max-reduction so that no rank takes the peer path alone).
+void setup_p2p(DistCtx& ctx, double* L, cudaStream_t st) {
+    const int world = ctx.world;
+    const char* env = getenv("LRN_DIST_P2P");
+    int ok = (env && atoi(env) == 0) ? 0 : 1;
+    if (world < 2) ok = 0;
+    for (void* m : ctx.ipc_opened) cudaIpcCloseMemHandle(m);
+    ctx.ipc_opened.clear();
+    ctx.flags = reinterpret_cast<int*>(ctx.xb.p + ctx.flags_off);
+    IpcPacket mine;
+    std::memset(&mine, 0, sizeof mine);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    mine.dev = dev;
+    mine.pid = (long long)getpid();
+    mine.px = (unsigned long long)ctx.xb.p; mine.pl = (unsigned long long)L;
+    mine.ox = alloc_offset(ctx.xb.p); mine.ol = alloc_offset(L);
+    if (ok) {
+        if (cudaIpcGetMemHandle(&mine.hx, ctx.xb.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.hl, L) != cudaSuccess) {
+            cudaGetLastError();
+            mine.pid = -1;                       // this rank cannot export: everybody falls back
+        }
+    }
+    static_assert(sizeof(IpcPacket) <= 256, "IpcPacket must fit the exchange slot");
+    DevBuf<char> sb(256), rb((size_t)256 * world);
+    LRN_CUDA(cudaMemcpyAsync(sb.p, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    LRN_NCCL(nccl_api().AllGather(sb.p, rb.p, 256, ncclChar, ctx.comm, st));
+    std::vector<char> all((size_t)256 * world);
+    LRN_CUDA(cudaMemcpyAsync(all.data(), rb.p, all.size(), cudaMemcpyDeviceToHost, st));
+    LRN_CUDA(cudaStreamSynchronize(st));
+    ctx.peer_xb.assign(world, nullptr); ctx.peer_L.assign(world, nullptr); ctx.peer_flags.assign(world, nullptr);
+    for (int r = 0; r < world && ok; r++) {
+        IpcPacket pk;
+        std::memcpy(&pk, all.data() + (size_t)256 * r, sizeof pk);
+        if (pk.pid < 0) { ok = 0; break; }
+        if (r == ctx.rank) {
+            ctx.peer_xb[r] = ctx.xb.p; ctx.peer_L[r] = L;
+        } else if (pk.pid == mine.pid) {         // same process (lrn_create_multi): plain peer access
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, dev, pk.dev);
+            if (!can) { ok = 0; break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(pk.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+            cudaGetLastError();
+            ctx.peer_xb[r] = (double*)pk.px; ctx.peer_L[r] = (double*)pk.pl;
+        } else {
+            void *mx = nullptr, *ml = nullptr;
+            if (cudaIpcOpenMemHandle(&mx, pk.hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&ml, pk.hl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                for (void* m : {mx, ml}) if (m) cudaIpcCloseMemHandle(m);
+                ok = 0;
+                break;
+            }
+            ctx.ipc_opened.push_back(mx); ctx.ipc_opened.push_back(ml);
+            ctx.peer_xb[r] = (double*)((char*)mx + pk.ox); ctx.peer_L[r] = (double*)((char*)ml + pk.ol);
+        }
+        ctx.peer_flags[r] = reinterpret_cast<int*>(ctx.peer_xb[r] + ctx.flags_off);
+    }
+    // agree: every rank must have succeeded
+    int* dflag = ctx.infos.p;
+    const int bad = ok ? 0 : 1;
+    LRN_CUDA(cudaMemcpyAsync(dflag, &bad, sizeof(int), cudaMemcpyHostToDevice, st));
+    LRN_NCCL(nccl_api().AllReduce(dflag, dflag, 1, ncclInt32, ncclMax, ctx.comm, st));
+    int anybad = 1;
+    LRN_CUDA(cudaMemcpyAsync(&anybad, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LRN_CUDA(cudaStreamSynchronize(st));
+    ctx.p2p = anybad ? 0 : 1;
+    ctx.L_mapped = L;
+    if (ctx.p2p) {
+        ctx.d_peer_xb.upload(ctx.peer_xb, st); ctx.d_peer_L.upload(ctx.peer_L, st); ctx.d_peer_flags.upload(ctx.peer_flags, st);
+        LRN_CUDA(cudaMemsetAsync(ctx.flags, 0, 66 * sizeof(int), st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        // nobody may push before everybody has cleared its flags
+        LRN_NCCL(nccl_api().AllReduce(dflag, dflag, 1, ncclInt32, ncclMax, ctx.comm, st));
+        LRN_CUDA(cudaStreamSynchronize(st));
+        ctx.epoch = 0;
+    }
+    if (getenv("LRN_DIST_TRACE") && ctx.rank == 0)
+        fprintf(stderr, "[lrn dist] panel exchange: %s\n", ctx.p2p ? "peer memory (NVLink P2P pushes + flags)" : "NCCL broadcast / all-gather");
 }
 
 // first row block >= p owned by `rank`, and how many of its blocks are >= p
@@ -123,10 +306,16 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
     const int nblk = (int)cdiv(n, pw);
     const int maxcnt0 = (int)cdiv(nblk, world);
     const size_t blk = (size_t)pw * pw, ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
-    if (ctx.xb.n < 2 * blk + ndmax) ctx.xb.alloc(2 * blk + ndmax);     // X | 64 x 64 inverse blocks | scratch of the inversion
+    // X | 64 x 64 inverse blocks | scratch of the inversion | flag words of the peer-memory exchange
+    if (ctx.xb.n < 2 * blk + ndmax + 64) { ctx.xb.alloc(2 * blk + ndmax + 64); ctx.flags_off = 2 * blk + ndmax; ctx.p2p = -1; }
     if (ctx.sendbuf.n < (size_t)maxcnt0 * blk) ctx.sendbuf.alloc((size_t)maxcnt0 * blk);
     if (ctx.recvbuf.n < (size_t)maxcnt0 * blk * world) ctx.recvbuf.alloc((size_t)maxcnt0 * blk * world);
     if (ctx.infos.n < (size_t)world) ctx.infos.alloc(world);
+    if (ctx.p2p < 0 || (ctx.p2p == 1 && ctx.L_mapped != A)) setup_p2p(ctx, A, st);     // collective, once per factor matrix
+    const bool p2p = ctx.p2p == 1;
+    const int stamp0 = (int)(ctx.epoch * (nblk + 1));
+    unsigned int* ctr0 = reinterpret_cast<unsigned int*>(ctx.flags ? ctx.flags + 64 : nullptr);
+    unsigned int* ctr1 = reinterpret_cast<unsigned int*>(ctx.flags ? ctx.flags + 65 : nullptr);
     ensure_aux(work);
     cudaStream_t sp = work.aux;                     // panel stream (high priority): diagonal block, broadcast, row solves, all-gather
     cudaEvent_t evStart = work.ev[0], evU = work.ev[1], evB = work.ev[2];
@@ -159,7 +348,19 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
             LRN_CUDA(cudaMemcpyAsync(xd, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
         }
         mark(sp, 1);
-        if (world > 1) LRN_NCCL(nccl_api().Broadcast(ctx.xb.p, ctx.xb.p, blk + ndmax, ncclDouble, owner, ctx.comm, sp));
+        const int stamp = stamp0 + p + 1;
+        if (p2p) {
+            // the owner pushes the inverse (+ its 64 x 64 inverse blocks) into every peer's xb and raises their flag 0
+            if (rank == owner) {
+                k_push_vec<<<96, 256, 0, sp>>>(ctx.xb.p, ctx.d_peer_xb.p, world, rank, blk + ndmax, ctx.d_peer_flags.p, 0, stamp, ctr0);
+                LRN_CHECK_LAUNCH();
+            } else {
+                k_wait_flags<<<1, 32, 0, sp>>>(ctx.flags, 0, 1, stamp);
+                LRN_CHECK_LAUNCH();
+            }
+        } else if (world > 1) {
+            LRN_NCCL(nccl_api().Broadcast(ctx.xb.p, ctx.xb.p, blk + ndmax, ncclDouble, owner, ctx.comm, sp));
+        }
         mark(sp, 2);
         if (rank != owner) LRN_CUDA(cudaMemcpyAsync(dk, xd, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
         const int maxcnt = (int)cdiv(nblk - p, world);
@@ -194,15 +395,27 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
                 }
             }
             mark(sp, 3);
-            const double* src = ctx.sendbuf.p;
-            if (world > 1) {
-                LRN_NCCL(nccl_api().AllGather(ctx.sendbuf.p, ctx.recvbuf.p, (size_t)maxcnt * blk, ncclDouble, ctx.comm, sp));
-                src = ctx.recvbuf.p;
+            if (p2p) {
+                // every rank stores its solved blocks at their final place in EVERY rank's L (its own included) over NVLink,
+                // raises flag 1 + rank everywhere, then waits until the blocks of all ranks have landed here
+                dim3 grid((unsigned)cdiv(pw / 2, 128), (unsigned)w, (unsigned)std::max(cnt, 1));
+                k_push_blocks<<<grid, 128, 0, sp>>>(ctx.sendbuf.p, ctx.d_peer_L.p, world, lda, n, c0, w, pw, f, cnt, ctx.d_peer_flags.p,
+                                                    1 + rank, stamp, ctr1);
+                LRN_CHECK_LAUNCH();
+                mark(sp, 4);
+                k_wait_flags<<<1, 64, 0, sp>>>(ctx.flags, 1, world, stamp);
+                LRN_CHECK_LAUNCH();
+            } else {
+                const double* src = ctx.sendbuf.p;
+                if (world > 1) {
+                    LRN_NCCL(nccl_api().AllGather(ctx.sendbuf.p, ctx.recvbuf.p, (size_t)maxcnt * blk, ncclDouble, ctx.comm, sp));
+                    src = ctx.recvbuf.p;
+                }
+                mark(sp, 4);
+                dim3 grid((unsigned)cdiv(pw, 256), (unsigned)w, (unsigned)(world * maxcnt));
+                k_unpack_blocks<<<grid, 256, 0, sp>>>(src, A, lda, n, c0, w, pw, p, world, maxcnt, nblk);
+                LRN_CHECK_LAUNCH();
             }
-            mark(sp, 4);
-            dim3 grid((unsigned)cdiv(pw, 256), (unsigned)w, (unsigned)(world * maxcnt));
-            k_unpack_blocks<<<grid, 256, 0, sp>>>(src, A, lda, n, c0, w, pw, p, world, maxcnt, nblk);
-            LRN_CHECK_LAUNCH();
             mark(sp, 5);
         }
         LRN_CUDA(cudaEventRecord(evB, sp));
@@ -242,6 +455,11 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
                             "next-col update %.2f  rest update %.2f | first-to-last event %.2f ms\n",
                     world, n, sum[0], sum[1], sum[2], sum[3], sum[4], sum[6], sum[10], sum[11], total);
         for (auto& v : tev) cudaEventDestroy(v.e);
+    }
+    ctx.epoch++;
+    if (p2p) {                                     // a peer that never answered: report instead of returning a wrong factor
+        k_check_timeout<<<1, 1, 0, st>>>(ctx.flags, info);
+        LRN_CHECK_LAUNCH();
     }
     // the first failing pivot index is known to the owner of that block only: take the smallest non-zero over ranks
     if (world > 1) {

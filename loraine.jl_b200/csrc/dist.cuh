@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include <nccl.h>
+#include <vector>
 
 namespace lrn {
 
@@ -28,6 +29,21 @@ struct DistCtx {
     DevBuf<double> xb;                 // broadcast buffer: inverse of the current diagonal block + its 64 x 64 inverse blocks
     DevBuf<double> sendbuf, recvbuf;   // solved row blocks of the current panel: mine / everybody's (ncclAllGather)
     DevBuf<int> infos;                 // world pivot flags
+    // ---- peer-memory exchange (NVLink P2P through CUDA IPC or in-process peer access) ------------------------------------
+    // Every rank maps the other ranks' xb (diagonal-block inverse), factor matrix L and flag words.  The owner of a diagonal
+    // block PUSHES its inverse into every peer's xb and every rank PUSHES its solved row blocks of the panel straight to their
+    // final place in every peer's L (no staging, no unpack pass), each followed by a flag store that the receivers poll on.
+    int p2p = -1;                      // -1 not tried, 0 unavailable (NCCL broadcast / all-gather are used), 1 active
+    std::vector<double*> peer_xb, peer_L;
+    std::vector<int*> peer_flags;
+    size_t flags_off = 0;              // offset (doubles) of the flag words inside xb
+    std::vector<void*> ipc_opened;     // mappings to close
+    const double* L_mapped = nullptr;  // the factor matrix the peers mapped (a different matrix needs a new exchange)
+    int* flags = nullptr;              // lives at the end of xb (one mapping): [0] X arrived (step stamp); [1 + r] blocks of rank r
+                                       // arrived; [63] time-out marker; [64], [65] completion counters of the push kernels
+    DevBuf<double*> d_peer_xb, d_peer_L;
+    DevBuf<int*> d_peer_flags;
+    long long epoch = 0;               // factorisations so far (stamps are epoch * (nblk + 1) + step + 1: never reset)
     ~DistCtx();
 };
 

@@ -997,6 +997,7 @@ int32_t lrn_schur_factor(lrn_handle_t h) {
             LRN_CUDA(cudaMemcpyAsync(&info, h->cholH.info_ptr(), sizeof(int), cudaMemcpyDeviceToHost, st));
             LRN_CUDA(cudaStreamSynchronize(st));
         }
+        LRN_REQUIRE(info >= 0, "distributed factorisation: a peer did not deliver its part of a panel in time (peer-memory exchange)");
         h->have_factor = (info == 0);
         return info;
     });
