@@ -793,9 +793,7 @@ void chol_build_tinv(const double* L, int n, int lda, CholWork& work, cudaStream
     work.tinv_for = L;
 }
 
-void chol_solve(const double* L, int n, int lda, CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {
-    if (n <= 0) return;
-    if (work.tinv_for != L) chol_build_tinv(L, n, lda, work, st);
+static void chol_solve_enqueue(const double* L, int n, int lda, CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {
     const int nstep = (int)cdiv(n, SW);
     for (int dir = 0; dir < 2; dir++) {
         if (!(which & (dir ? 2 : 1))) continue;
@@ -814,6 +812,52 @@ void chol_solve(const double* L, int n, int lda, CholWork& work, double* x, doub
         }
         LRN_CUDA(cudaMemcpyAsync(x, tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
+}
+
+void chol_solve(const double* L, int n, int lda, CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {
+    if (n <= 0) return;
+    if (work.tinv_for != L) chol_build_tinv(L, n, lda, work, st);
+    CholWork::SolveGraph& G = work.sgraph[which & 3];
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {        // already inside somebody else's capture (the PCG body): plain launches
+        chol_solve_enqueue(L, n, lda, work, x, tmp, which, st);
+        return;
+    }
+    const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && !gemm_profile_active() &&
+                            n >= 4 * SW && !G.broken;
+    const bool same = G.exec && G.L == L && G.tinv == work.tinv.p && G.x == x && G.tmp == tmp && G.n == n && G.lda == lda;
+    if (capturable && same) {
+        LRN_CUDA(cudaGraphLaunch(G.exec, st));
+        g_kernel_launches.fetch_add(G.nodes);
+        return;
+    }
+    if (!capturable || !G.warm) {                    // small systems, uncapturable streams, and the first solve (eager warm-up)
+        chol_solve_enqueue(L, n, lda, work, x, tmp, which, st);
+        G.warm = true;
+        return;
+    }
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        cudaGraph_t graph = nullptr;
+        const long long before = g_kernel_launches.load();
+        try { chol_solve_enqueue(L, n, lda, work, x, tmp, which, st); } catch (...) { ok = false; }
+        if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+        G.nodes = g_kernel_launches.load() - before;
+        g_kernel_launches.fetch_sub(G.nodes);
+        if (ok && cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) { ok = false; G.exec = nullptr; }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    if (!ok) {
+        cudaGetLastError();
+        G.broken = true;
+        chol_solve_enqueue(L, n, lda, work, x, tmp, which, st);
+        return;
+    }
+    G.L = L; G.tinv = work.tinv.p; G.x = x; G.tmp = tmp; G.n = n; G.lda = lda;
+    LRN_CUDA(cudaGraphLaunch(G.exec, st));
+    g_kernel_launches.fetch_add(G.nodes);
 }
 
 void trsm_left_lower_trans(const double* L, int n, int lda, const CholWork& work, double* Y, int ldy, int ncols, cudaStream_t st) {

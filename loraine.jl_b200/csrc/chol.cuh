@@ -17,6 +17,15 @@ struct CholWork {
     DevBuf<double> pout;      // out-of-place panel solve result (rows x kb)
     DevBuf<double> tinv, tscr; // inverses of the 256 x 256 diagonal blocks of L (triangular solves) + 64 x 64 scratch per block
     const double* tinv_for = nullptr;   // factor the inverses belong to (reset by every factorisation)
+    // the launch sequence of a triangular solve (2 launches per 256 unknowns) only depends on (L, n, lda, x, tmp, which): it is
+    // captured once as a CUDA graph and replayed (the solves are bound by launch latency, not by HBM)
+    struct SolveGraph {
+        cudaGraphExec_t exec = nullptr;
+        const double* L = nullptr; const double* tinv = nullptr; double* x = nullptr; double* tmp = nullptr;
+        int n = 0, lda = 0;
+        long long nodes = 0;
+        bool warm = false, broken = false;
+    } sgraph[4];                  // indexed by `which` (1 forward, 2 backward, 3 both)
     cudaStream_t aux = nullptr;   // high-priority side stream (panel factorisation + broadcast look-ahead in multi-GPU runs)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n = 0;

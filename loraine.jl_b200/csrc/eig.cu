@@ -775,7 +775,9 @@ void SweepGraphs::reset() {
 // `advance` advances them without enqueueing anything (after a replay).
 template <typename Body, typename Advance>
 static void run_sweep(SweepGraphs& G, int parity, cudaStream_t st, Body&& body, Advance&& advance) {
-    const bool graphs_ok = !G.broken && !gemm_profile_active();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) cudaStreamIsCapturing(st, &cap);
+    const bool graphs_ok = !G.broken && !gemm_profile_active() && cap == cudaStreamCaptureStatusNone;
     if (graphs_ok && G.exec[parity]) {
         LRN_CUDA(cudaGraphLaunch(G.exec[parity], st));
         g_kernel_launches.fetch_add(G.nodes[parity]);

@@ -158,8 +158,9 @@ void sp_B_times_G(cudaStream_t st, const SparseBlock& sb, const double* G, int l
 void sp_schur_pairs(cudaStream_t st, const SparseBlock& sb, int first, const double* W, int ldw, double* H, int ldh,
                     RowOwner own = RowOwner());
 // The same Schur term through the shared-memory staged kernel (pairs.cu); requires sb.pairs.ok.  All pairs of the block.
+// accumulate = false: H holds zeros where this block writes (first block of an assembly): plain stores instead of read-modify-write
 void sp_schur_pairs_staged(cudaStream_t st, const SparseBlock& sb, const double* W, int ldw, double* H, int ldh,
-                           RowOwner own = RowOwner());
+                           RowOwner own = RowOwner(), bool accumulate = true);
 // host: build sb.pairs from the by-constraint entry lists (0-based rowptr / p / q / value, symmetric storage required)
 void sp_build_pair_plan(SparseBlock& sb, const std::vector<int>& rowptr, const std::vector<int>& ep, const std::vector<int>& eq,
                         const std::vector<double>& ev, cudaStream_t st);

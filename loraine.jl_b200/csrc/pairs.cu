@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(PT, 1)
                          const int* __restrict__ gidx, const int* __restrict__ row_off, const int* __restrict__ row_c,
                          const double* __restrict__ rowA, int nbuckets, const int* __restrict__ b_first,
                          const int* __restrict__ b_ids, const int* __restrict__ b_eptr, const int2* __restrict__ e_pq,
-                         const double* __restrict__ e_w, RowOwner own) {
+                         const double* __restrict__ e_w, RowOwner own, int accumulate) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double sA[PAIR_ROWS * PAIR_MAXC * PAIR_MAXC];
     __shared__ int s_off[PAIR_ROWS], s_c[PAIR_ROWS];
@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(PT, 1)
                         acc = fma(e_w[f], bilinear<8>(smem + (size_t)pq.x * S + off, smem + (size_t)pq.y * S + off, A), acc);
                     }
                 }
-                dst[(size_t)r * ldh] += acc;
+                // every (j, k) of a block is produced exactly once: the first block of an assembly stores (H was cleared), later
+                // blocks add -- a plain store keeps the HBM round trip of a read-modify-write out of the dependency chain
+                if (accumulate) dst[(size_t)r * ldh] += acc;
+                else dst[(size_t)r * ldh] = acc;
             }
         }
     }
@@ -221,14 +224,16 @@ void sp_build_pair_plan(SparseBlock& sb, const std::vector<int>& rowptr, const s
     P.ok = true;
 }
 
-void sp_schur_pairs_staged(cudaStream_t st, const SparseBlock& sb, const double* W, int ldw, double* H, int ldh, RowOwner own) {
+void sp_schur_pairs_staged(cudaStream_t st, const SparseBlock& sb, const double* W, int ldw, double* H, int ldh, RowOwner own,
+                           bool accumulate) {
     const PairPlan& P = sb.pairs;
     LRN_REQUIRE(P.ok, "no staged pair plan for this block");
     static PerDeviceOnce once;
     once.run([&] { LRN_CUDA(cudaFuncSetAttribute(k_schur_pairs_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
     k_schur_pairs_staged<<<(unsigned)P.ngroups, PT, P.smem, st>>>(sb.m, W, ldw, H, ldh, P.g_r0.p, P.g_cnt.p, P.g_S.p, P.g_idx0.p,
                                                                  P.gidx.p, P.row_off.p, P.row_c.p, P.rowA.p, P.nbuckets,
-                                                                 P.b_first.p, P.b_ids.p, P.b_eptr.p, P.e_pq.p, P.e_w.p, own);
+                                                                 P.b_first.p, P.b_ids.p, P.b_eptr.p, P.e_pq.p, P.e_w.p, own,
+                                                                 accumulate ? 1 : 0);
     LRN_CHECK_LAUNCH();
 }
 

@@ -870,8 +870,11 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
         h->H_gathered = false;
         RowOwner own;                                  // multi-GPU: every rank assembles only the row blocks it owns
         own.rank = h->rank; own.world = h->world; own.pw = h->dist_pw;
+        bool first_block = true;                       // H is still all zeros
         for (auto& B : h->blk) {
             const int m = B.m, ld = B.ld;
+            const bool h_is_zero = first_block;
+            first_block = false;
             if (h->opt.datarank == -1) {
                 // BBBB += ((B G)(B G)').^2                                    (src/makeBBBB.jl:7-14)
                 sp_B_times_G(st, B.sp, B.G.p(), ld, h->BG.p(), h->BG.ld);
@@ -895,7 +898,7 @@ int32_t lrn_schur_assemble(lrn_handle_t h) {
                 }
                 // F3 for the remaining (sparse) matrices                       (src/makeBBBB.jl:139-213)
                 if (B.sp.pairs.ok && (h->use_staged_pairs == 1 || (h->use_staged_pairs < 0 && B.sp.npart >= 1024)))
-                    sp_schur_pairs_staged(st, B.sp, B.W.p(), ld, h->H.p(), h->H.ld, own);
+                    sp_schur_pairs_staged(st, B.sp, B.W.p(), ld, h->H.p(), h->H.ld, own, !(h_is_zero && B.sp.nF1 == 0));
                 else sp_schur_pairs(st, B.sp, B.sp.nF1, B.W.p(), ld, h->H.p(), h->H.ld, own);
             }
         }
