@@ -702,6 +702,7 @@ void ensure_aux(CholWork& work) {
     int lo = 0, hi = 0;
     LRN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     LRN_CUDA(cudaStreamCreateWithPriority(&work.aux, cudaStreamNonBlocking, hi));
+    LRN_CUDA(cudaStreamCreateWithPriority(&work.aux2, cudaStreamNonBlocking, hi));
     for (auto& e : work.ev) LRN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 

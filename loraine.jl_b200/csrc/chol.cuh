@@ -27,6 +27,7 @@ struct CholWork {
         bool warm = false, broken = false;
     } sgraph[4];                  // indexed by `which` (1 forward, 2 backward, 3 both)
     cudaStream_t aux = nullptr;   // high-priority side stream (panel factorisation + broadcast look-ahead in multi-GPU runs)
+    cudaStream_t aux2 = nullptr;  // second high-priority stream (distributed path: early factorisation of the next diagonal block)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n = 0;
     void ensure(int n_) {

@@ -72,14 +72,14 @@ constexpr long long P2P_SPIN_LIMIT = 4000000000LL;     // ~2 s of SM clocks: a l
 
 // copy `count` doubles (multiple of 2) from src to the same offset of every peer buffer, then publish `stamp` in every peer's
 // flag word `slot` (the last CTA to finish does it, after a system-wide fence)
-__global__ void k_push_vec(const double* src, double* const* __restrict__ peers, int world, int self, size_t count,
+__global__ void k_push_vec(const double* src, double* const* __restrict__ peers, int world, int self, size_t dst_off, size_t count,
                            int* const* __restrict__ peer_flags, int slot, int stamp, unsigned int* __restrict__ done_ctr) {
     const size_t n2 = count / 2;
     const double2* s2 = reinterpret_cast<const double2*>(src);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
         const double2 v = s2[i];
         for (int r = 0; r < world; r++)
-            if (r != self) reinterpret_cast<double2*>(peers[r])[i] = v;
+            if (r != self) reinterpret_cast<double2*>(peers[r] + dst_off)[i] = v;
     }
     __threadfence_system();
     __syncthreads();
@@ -231,7 +231,7 @@ void setup_p2p(DistCtx& ctx, double* L, cudaStream_t st) {
     int anybad = 1;
     LRN_CUDA(cudaMemcpyAsync(&anybad, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
     LRN_CUDA(cudaStreamSynchronize(st));
-    ctx.p2p = anybad ? 0 : 1;
+    ctx.p2p = anybad ? 0 : ((env && atoi(env) >= 2) ? 2 : 1);
     ctx.L_mapped = L;
     if (ctx.p2p) {
         ctx.d_peer_xb.upload(ctx.peer_xb, st); ctx.d_peer_L.upload(ctx.peer_L, st); ctx.d_peer_flags.upload(ctx.peer_flags, st);
@@ -243,7 +243,9 @@ void setup_p2p(DistCtx& ctx, double* L, cudaStream_t st) {
         ctx.epoch = 0;
     }
     if (getenv("LRN_DIST_TRACE") && ctx.rank == 0)
-        fprintf(stderr, "[lrn dist] panel exchange: %s\n", ctx.p2p ? "peer memory (NVLink P2P pushes + flags)" : "NCCL broadcast / all-gather");
+        fprintf(stderr, "[lrn dist] exchange mode %d: %s\n", ctx.p2p,
+                ctx.p2p == 2 ? "inverse and solved panel pushed over peer memory" :
+                ctx.p2p == 1 ? "inverse pushed over peer memory, solved panel through ncclAllGather" : "NCCL broadcast / all-gather");
 }
 
 // first row block >= p owned by `rank`, and how many of its blocks are >= p
@@ -306,25 +308,29 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
     const int nblk = (int)cdiv(n, pw);
     const int maxcnt0 = (int)cdiv(nblk, world);
     const size_t blk = (size_t)pw * pw, ndmax = (size_t)(pw / CHOL_DB) * CHOL_DB * CHOL_DB;
-    // X | 64 x 64 inverse blocks | scratch of the inversion | flag words of the peer-memory exchange
-    if (ctx.xb.n < 2 * blk + ndmax + 64) { ctx.xb.alloc(2 * blk + ndmax + 64); ctx.flags_off = 2 * blk + ndmax; ctx.p2p = -1; }
+    const size_t xhalf = 2 * blk + ndmax;            // one inverse buffer: X | 64 x 64 inverse blocks | scratch of the inversion
+    // two inverse buffers (step parity: X(p+1) is produced while X(p) is still being used) + flag words of the peer exchange
+    if (ctx.xb.n < 2 * xhalf + 64) { ctx.xb.alloc(2 * xhalf + 64); ctx.flags_off = 2 * xhalf; ctx.p2p = -1; }
     if (ctx.sendbuf.n < (size_t)maxcnt0 * blk) ctx.sendbuf.alloc((size_t)maxcnt0 * blk);
     if (ctx.recvbuf.n < (size_t)maxcnt0 * blk * world) ctx.recvbuf.alloc((size_t)maxcnt0 * blk * world);
     if (ctx.infos.n < (size_t)world) ctx.infos.alloc(world);
-    if (ctx.p2p < 0 || (ctx.p2p == 1 && ctx.L_mapped != A)) setup_p2p(ctx, A, st);     // collective, once per factor matrix
-    const bool p2p = ctx.p2p == 1;
+    if (ctx.p2p < 0 || (ctx.p2p >= 1 && ctx.L_mapped != A)) setup_p2p(ctx, A, st);     // collective, once per factor matrix
+    // exchange mode: 0 NCCL only; 1 (default) the 2 MB inverse travels over peer memory (latency-bound), the solved panel through
+    // ncclAllGather (bandwidth-bound: NCCL replicates inside the NVSwitch, a peer push sends world-1 copies); 2 everything pushed
+    const int mode = ctx.p2p;
+    const bool push_x = mode >= 1, push_panel = mode >= 2;
     const int stamp0 = (int)(ctx.epoch * (nblk + 1));
     unsigned int* ctr0 = reinterpret_cast<unsigned int*>(ctx.flags ? ctx.flags + 64 : nullptr);
     unsigned int* ctr1 = reinterpret_cast<unsigned int*>(ctx.flags ? ctx.flags + 65 : nullptr);
     ensure_aux(work);
-    cudaStream_t sp = work.aux;                     // panel stream (high priority): diagonal block, broadcast, row solves, all-gather
-    cudaEvent_t evStart = work.ev[0], evU = work.ev[1], evB = work.ev[2];
+    cudaStream_t sp = work.aux;    // panel stream: X arrival, row solves, exchange of the solved panel
+    cudaStream_t sq = work.aux2;   // diagonal stream: early update + factorisation + inversion of the NEXT diagonal block
+    cudaEvent_t evStart = work.ev[0], evU = work.ev[1], evB = work.ev[2], evS = work.ev[3], evD = work.ev[4], evU2 = work.ev[5];
     int* info = work.info_ptr();
     LRN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     LRN_CUDA(cudaEventRecord(evStart, st));
     LRN_CUDA(cudaStreamWaitEvent(sp, evStart, 0));
-    double* X = ctx.xb.p;
-    double* xd = ctx.xb.p + blk;
+    LRN_CUDA(cudaStreamWaitEvent(sq, evStart, 0));
     // optional timeline (LRN_DIST_TRACE=1): CUDA events around every stage of the panel chain and of the update, summed per stage
     static const bool trace = getenv("LRN_DIST_TRACE") != nullptr;
     struct Ev { cudaEvent_t e; int stage; };
@@ -336,37 +342,49 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
         LRN_CUDA(cudaEventRecord(v.e, s_));
         tev.push_back(v);
     };
-    for (int p = 0; p < nblk; p++) {
-        const int c0 = p * pw, w = std::min(pw, n - c0), owner = p % world;
+    auto xbuf = [&](int p) { return ctx.xb.p + (size_t)(p & 1) * xhalf; };
+    // factor diagonal block q (already fully updated), build the inverse of its factor and hand it to the other ranks
+    auto factor_and_publish = [&](int q) {
+        const int c0 = q * pw, w = std::min(pw, n - c0);
+        double* X = xbuf(q);
         double* dk = work.dinv.p + (size_t)(c0 / CHOL_DB) * CHOL_DB * CHOL_DB;
         const int nd = (int)cdiv(w, CHOL_DB) * CHOL_DB * CHOL_DB;
-        // ---- panel chain of step p ------------------------------------------------------------------------------------
-        if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));             // column block p has received the update of step p-1
-        mark(sp, 0);
-        if (rank == owner) {
-            chol_diag_block(A + (size_t)c0 * lda + c0, lda, w, dk, X, pw, ctx.xb.p + blk + ndmax, info, c0, sp);
-            LRN_CUDA(cudaMemcpyAsync(xd, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
+        chol_diag_block(A + (size_t)c0 * lda + c0, lda, w, dk, X, pw, X + blk + ndmax, info, c0, sq);
+        LRN_CUDA(cudaMemcpyAsync(X + blk, dk, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sq));
+        if (push_x) {
+            k_push_vec<<<96, 256, 0, sq>>>(X, ctx.d_peer_xb.p, world, rank, (size_t)(q & 1) * xhalf, blk + ndmax, ctx.d_peer_flags.p, 0,
+                                           stamp0 + q + 1, ctr0);
+            LRN_CHECK_LAUNCH();
         }
-        mark(sp, 1);
+        LRN_CUDA(cudaEventRecord(evD, sq));
+    };
+    if (rank == 0 % world) factor_and_publish(0);
+    for (int p = 0; p < nblk; p++) {
+        const int c0 = p * pw, w = std::min(pw, n - c0), owner = p % world;
+        double* X = xbuf(p);
+        double* xd = X + blk;
+        double* dk = work.dinv.p + (size_t)(c0 / CHOL_DB) * CHOL_DB * CHOL_DB;
+        const int nd = (int)cdiv(w, CHOL_DB) * CHOL_DB * CHOL_DB;
         const int stamp = stamp0 + p + 1;
-        if (p2p) {
-            // the owner pushes the inverse (+ its 64 x 64 inverse blocks) into every peer's xb and raises their flag 0
-            if (rank == owner) {
-                k_push_vec<<<96, 256, 0, sp>>>(ctx.xb.p, ctx.d_peer_xb.p, world, rank, blk + ndmax, ctx.d_peer_flags.p, 0, stamp, ctr0);
-                LRN_CHECK_LAUNCH();
-            } else {
+        // ---- panel chain of step p ------------------------------------------------------------------------------------
+        if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sp, evU, 0));             // my rows of column block p have the update of step p-1
+        mark(sp, 0);
+        if (rank == owner) LRN_CUDA(cudaStreamWaitEvent(sp, evD, 0));     // (my own factorisation of block p, on the diagonal stream)
+        mark(sp, 1);
+        if (push_x) {
+            if (rank != owner) {                                          // the owner pushed X(p) into xbuf(p) and raised flag 0
                 k_wait_flags<<<1, 32, 0, sp>>>(ctx.flags, 0, 1, stamp);
                 LRN_CHECK_LAUNCH();
             }
         } else if (world > 1) {
-            LRN_NCCL(nccl_api().Broadcast(ctx.xb.p, ctx.xb.p, blk + ndmax, ncclDouble, owner, ctx.comm, sp));
+            LRN_NCCL(nccl_api().Broadcast(X, X, blk + ndmax, ncclDouble, owner, ctx.comm, sp));
         }
-        mark(sp, 2);
         if (rank != owner) LRN_CUDA(cudaMemcpyAsync(dk, xd, (size_t)nd * sizeof(double), cudaMemcpyDeviceToDevice, sp));
+        mark(sp, 2);
         const int maxcnt = (int)cdiv(nblk - p, world);
+        const int f = first_block(p, rank, world), cnt = count_blocks(p, rank, world, nblk);
         if (p + 1 < nblk || world > 1) {
             // my row blocks g > p of the panel:  send[z] = A[g rows, panel p] * X^T ; the owner's slot 0 is the diagonal block itself
-            const int f = first_block(p, rank, world), cnt = count_blocks(p, rank, world, nblk);
             const int z0 = (rank == owner) ? 1 : 0;
             if (rank == owner) {
                 dim3 grid((unsigned)cdiv(w, 256), (unsigned)w);
@@ -394,8 +412,26 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
                     gemm(g, sp);
                 }
             }
-            mark(sp, 3);
-            if (p2p) {
+        }
+        LRN_CUDA(cudaEventRecord(evS, sp));
+        mark(sp, 3);
+        // ---- diagonal stream: the owner of block p+1 has just solved ITS OWN rows of panel p, which is all the update of its
+        //      diagonal block needs: update, factor, invert and publish X(p+1) while the panel of step p is still being exchanged
+        if (p + 1 < nblk && rank == (p + 1) % world) {
+            const int c1 = c0 + pw, hb1 = std::min(pw, n - c1);
+            LRN_CUDA(cudaStreamWaitEvent(sq, evS, 0));
+            if (p > 0) LRN_CUDA(cudaStreamWaitEvent(sq, evU2, 0));        // column block p+1 has the update of step p-1
+            const double* Srow = ctx.sendbuf.p + (size_t)((p + 1 - f) / world) * blk;     // my solved block g = p+1
+            GemmParams g;
+            g.A = Srow; g.B = Srow; g.C = A + (size_t)c1 * lda + c1;
+            g.M = hb1; g.N = hb1; g.K = w; g.lda = pw; g.ldb = pw; g.ldc = lda;
+            g.transB = true; g.alpha = -1.0; g.beta = 1.0; g.lower = 1;
+            gemm(g, sq);
+            factor_and_publish(p + 1);
+        }
+        // ---- exchange of the solved panel -----------------------------------------------------------------------------------
+        if (p + 1 < nblk || world > 1) {
+            if (push_panel) {
                 // every rank stores its solved blocks at their final place in EVERY rank's L (its own included) over NVLink,
                 // raises flag 1 + rank everywhere, then waits until the blocks of all ranks have landed here
                 dim3 grid((unsigned)cdiv(pw / 2, 128), (unsigned)w, (unsigned)std::max(cnt, 1));
@@ -421,28 +457,34 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
         LRN_CUDA(cudaEventRecord(evB, sp));
         LRN_CUDA(cudaStreamWaitEvent(st, evB, 0));
         if (p + 1 >= nblk) break;
-        // ---- trailing update with panel p: next column block first (so that the panel chain of step p+1 can start) --------------
+        // ---- trailing update with panel p on the main stream, two column blocks ahead first: column block p+1 (my rows are
+        //      solved next; its diagonal block was already updated on the diagonal stream), column block p+2 (its diagonal block
+        //      is factored during step p+1), then the rest
         const double* P = A + (size_t)c0 * lda;                            // column panel p: rows are global
-        const int c1 = c0 + pw, c2 = std::min(n, c1 + pw);
+        const int c1 = c0 + pw, c2 = std::min(n, c1 + pw), c3 = std::min(n, c2 + pw);
         mark(st, 10);
-        row_block_gemm(st, n, pw, rank, world, p + 1, P, lda, P, lda, A, lda, c1, c2, w, -1.0, 1.0, 0, false);
+        row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c1, c2, w, -1.0, 1.0, 0, false);
         LRN_CUDA(cudaEventRecord(evU, st));
+        if (c2 < n) row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c2, c3, w, -1.0, 1.0, 0, true);
+        LRN_CUDA(cudaEventRecord(evU2, st));
         mark(st, 11);
-        if (c2 < n) row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c2, n, w, -1.0, 1.0, 0, true);
+        if (c3 < n) row_block_gemm(st, n, pw, rank, world, p + 3, P, lda, P, lda, A, lda, c3, n, w, -1.0, 1.0, 0, true);
         mark(st, 12);
     }
+    LRN_CUDA(cudaEventRecord(evD, sq));
+    LRN_CUDA(cudaStreamWaitEvent(st, evD, 0));
     if (trace) {
         LRN_CUDA(cudaStreamSynchronize(sp));
+        LRN_CUDA(cudaStreamSynchronize(sq));
         LRN_CUDA(cudaStreamSynchronize(st));
-        // stage sums: 0->1 diagonal block, 1->2 broadcast, 2->3 row solves, 3->4 all-gather, 4->5 unpack, 5->next 0 wait for the update
+        // stage sums on the panel stream: 0->1 wait for my own diagonal block, 1->2 X arrival, 2->3 row solves, 3->4 exchange,
+        // 4->5 unpack / flag wait, 5->next 0 wait for the update of the main stream
         double sum[16] = {0};
         for (size_t i = 0; i + 1 < tev.size(); i++) {
-            const int a = tev[i].stage, b = tev[i + 1].stage;
+            const int a = tev[i].stage, b2 = tev[i + 1].stage;
             float ms = 0.f;
-            if (a < 10 && b < 10 && b == a + 1) { cudaEventElapsedTime(&ms, tev[i].e, tev[i + 1].e); sum[a] += ms; }
-            else if (a >= 10 && b == a + 1) { cudaEventElapsedTime(&ms, tev[i].e, tev[i + 1].e); sum[a] += ms; }
+            if (b2 == a + 1 && a != 5) { cudaEventElapsedTime(&ms, tev[i].e, tev[i + 1].e); sum[a] += ms; }
         }
-        // gaps of the panel stream between the end of one chain and the start of the next (waiting for the update of the main stream)
         const Ev* last5 = nullptr;
         for (auto& v : tev) {
             if (v.stage == 5) last5 = &v;
@@ -451,13 +493,13 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
         float total = 0.f;
         if (!tev.empty()) cudaEventElapsedTime(&total, tev.front().e, tev.back().e);
         if (rank == 0)
-            fprintf(stderr, "[lrn dist trace] world %d n %d: diag %.2f  bcast %.2f  solve %.2f  allgather %.2f  unpack %.2f  panel-stream wait %.2f | "
-                            "next-col update %.2f  rest update %.2f | first-to-last event %.2f ms\n",
-                    world, n, sum[0], sum[1], sum[2], sum[3], sum[4], sum[6], sum[10], sum[11], total);
+            fprintf(stderr, "[lrn dist trace] world %d n %d mode %d: own-diag wait %.2f  X arrival %.2f  solve %.2f  exchange %.2f  unpack/flags %.2f  "
+                            "panel-stream wait %.2f | 2 look-ahead column blocks %.2f  rest update %.2f | first-to-last event %.2f ms\n",
+                    world, n, mode, sum[0], sum[1], sum[2], sum[3], sum[4], sum[6], sum[10], sum[11], total);
         for (auto& v : tev) cudaEventDestroy(v.e);
     }
     ctx.epoch++;
-    if (p2p) {                                     // a peer that never answered: report instead of returning a wrong factor
+    if (push_x) {                                  // a peer that never answered: report instead of returning a wrong factor
         k_check_timeout<<<1, 1, 0, st>>>(ctx.flags, info);
         LRN_CHECK_LAUNCH();
     }
