@@ -463,9 +463,9 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
         const double* P = A + (size_t)c0 * lda;                            // column panel p: rows are global
         const int c1 = c0 + pw, c2 = std::min(n, c1 + pw), c3 = std::min(n, c2 + pw);
         mark(st, 10);
-        row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c1, c2, w, -1.0, 1.0, 0, false);
+        // (one launch for both look-ahead column blocks: N = 1024 keeps the strided-batch product on the TMA-fed kernel)
+        row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c1, c3, w, -1.0, 1.0, 0, true);
         LRN_CUDA(cudaEventRecord(evU, st));
-        if (c2 < n) row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c2, c3, w, -1.0, 1.0, 0, true);
         LRN_CUDA(cudaEventRecord(evU2, st));
         mark(st, 11);
         if (c3 < n) row_block_gemm(st, n, pw, rank, world, p + 3, P, lda, P, lda, A, lda, c3, n, w, -1.0, 1.0, 0, true);
