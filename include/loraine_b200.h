@@ -169,6 +169,9 @@ int32_t lrn_apply_operator(lrn_handle_t h, int32_t kind, const double* x, double
 #define LRN_T_COUNT 12
 /* accumulated device milliseconds (CUDA events on the library stream) and call counts per phase; reset != 0 clears */
 int32_t lrn_timers(lrn_handle_t h, double* ms, int64_t* calls, int32_t reset);
+/* name of a phase under the reference's TimerOutputs section names where one exists ("prep W", "BBBBs" -- "BBBB_rank1" when
+ * rank1 != 0 --, "prep W SVD", "prec", src/makeBBBB.jl:2,30, src/prepare_W.jl:37, src/Solvers.jl:676); NULL when out of range */
+const char* lrn_timer_name(int32_t phase, int32_t rank1);
 /* number of kernels launched by the library through this handle's process so far */
 int64_t lrn_kernel_launches(void);
 /* change an option after creation (the reference mutates solver.aamat / solver.preconditioner in the hybrid switch,

@@ -67,6 +67,7 @@ def lib():
         "lrn_apply_operator": (i32, [vp, i32, pdbl, pdbl]),
         "lrn_timers": (i32, [vp, pdbl, pi64, i32]),
         "lrn_kernel_launches": (i64, []),
+        "lrn_timer_name": (C.c_char_p, [i32, i32]),
         "lrn_stats": (i32, [vp, pi64]),
         "lrn_set_option": (i32, [vp, C.c_char_p, dbl]),
         "lrn_create_from_triplets": (i32, [C.POINTER(vp), i64, i64, pi64, i64, pi64, pi64, pi64, pi64, pdbl, pdbl,
@@ -97,7 +98,7 @@ DECLARED_SYMBOLS = ["lrn_default_options", "lrn_create", "lrn_set_block_AA", "lr
                     "lrn_schur_solve", "lrn_prec_prepare", "lrn_pcg", "lrn_find_step", "lrn_sigma_trace", "lrn_dimacs",
                     "lrn_get_array", "lrn_apply_operator", "lrn_timers", "lrn_kernel_launches", "lrn_stats", "lrn_set_option",
                     "lrn_dist_unique_id", "lrn_dist_init", "lrn_create_multi",
-                    "lrn_create_from_triplets", "lrn_load_sdpa", "lrn_initial_point", "lrn_get_dims"]
+                    "lrn_create_from_triplets", "lrn_load_sdpa", "lrn_initial_point", "lrn_get_dims", "lrn_timer_name"]
 
 DEBUG_SYMBOLS = ["lrn_dbg_gemm", "lrn_dbg_cholesky", "lrn_dbg_eig_small", "lrn_dbg_svd", "lrn_dbg_lanczos",
                  "lrn_dbg_batched_lambda_min", "lrn_dbg_peak", "lrn_dbg_gemm_profile", "lrn_dbg_set_shard", "lrn_dbg_compare",

@@ -1365,6 +1365,14 @@ int32_t lrn_timers(lrn_handle_t h, double* ms, int64_t* calls, int32_t reset) {
     });
 }
 
+const char* lrn_timer_name(int32_t phase, int32_t rank1) {
+    static const char* names[LRN_T_COUNT] = {"prep W", "residuals", "BBBBs", "RHS", "cholesky", "solve", "find_step", "prec",
+                                             "CG", "check_convergence", "prep W SVD", "eigmin"};
+    if (phase < 0 || phase >= LRN_T_COUNT) return nullptr;
+    if (phase == LRN_T_ASSEMBLE && rank1) return "BBBB_rank1";
+    return names[phase];
+}
+
 int32_t lrn_set_option(lrn_handle_t h, const char* name, double value) {
     LRN_GROUP(h, lrn_set_option(m_, name, value));
     return guarded(h, [&]() -> int32_t {

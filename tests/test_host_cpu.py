@@ -28,6 +28,16 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(_lib.DECLARED_SYMBOLS) <= set(names)
 
 
+def test_timer_names_follow_the_reference_sections(pkg):
+    """TimerOutputs section names of the reference (src/makeBBBB.jl:2,30, src/prepare_W.jl:37, src/Solvers.jl:676)."""
+    from loraine_jl_b200 import _lib
+    L = _lib.lib()
+    names = [L.lrn_timer_name(i, 0).decode() for i in range(len(_lib.T_NAMES))]
+    assert names[2] == "BBBBs" and L.lrn_timer_name(2, 1) == b"BBBB_rank1"
+    assert names[10] == "prep W SVD" and names[7] == "prec"
+    assert L.lrn_timer_name(99, 0) is None
+
+
 def test_create_without_gpu_fails_loudly(pkg):
     import torch
     if torch.cuda.is_available():
