@@ -581,10 +581,10 @@ __global__ void tinv_diag_kernel(const double* __restrict__ dinv, double* __rest
 
 __global__ void __launch_bounds__(1024)
     trsv_diag_kernel(const double* __restrict__ X, int jb, const double* __restrict__ rhs, double* __restrict__ sol, int dir,
-                     const double* __restrict__ Xnext, const double* __restrict__ rhs2) {
+                     const double* __restrict__ Xnext) {
     __shared__ double xs[SW], red[4][SW];
     const int tid = threadIdx.x;
-    if (tid < SW) xs[tid] = (tid < jb) ? (rhs2 ? rhs[tid] + rhs2[tid] : rhs[tid]) : 0.0;
+    if (tid < SW) xs[tid] = (tid < jb) ? rhs[tid] : 0.0;
     if (Xnext) {   // pull the next step's inverse block (512 KB) towards L2 while this step runs
         const char* pn = reinterpret_cast<const char*>(Xnext) + (size_t)tid * 512;
 #pragma unroll
@@ -645,12 +645,12 @@ __global__ void __launch_bounds__(1024)
 
 __global__ void __launch_bounds__(256)
     trsv_update_fwd_kernel(const double* __restrict__ L, int lda, int n, int j0, int jb, const double* __restrict__ y,
-                           double* __restrict__ rhs, int i_lo) {
+                           double* __restrict__ rhs) {
     __shared__ double ys[SW], red[4][64];
     const int tid = threadIdx.x, r = tid & 63, q = tid >> 6;
     ys[tid] = (tid < jb) ? y[tid] : 0.0;
     __syncthreads();
-    const int i = i_lo + blockIdx.x * 64 + r;            // rows [i_lo, n): the caller passes n = end of its row window
+    const int i = j0 + jb + blockIdx.x * 64 + r;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (i < n) {
         const int c0 = q * 64, c1 = min(jb, c0 + 64);
@@ -677,18 +677,18 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     trsv_update_bwd_kernel(const double* __restrict__ L, int lda, int j0, int jb, const double* __restrict__ y,
-                           double* __restrict__ rhs, int c_lo, int c_hi) {
+                           double* __restrict__ rhs) {
     __shared__ double ys[SW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     ys[tid] = (tid < jb) ? y[tid] : 0.0;
     __syncthreads();
     // 32 columns of L per CTA, 4 per warp, two at a time
-    const int ibase = c_lo + blockIdx.x * 32 + warp * 4;      // columns [c_lo, c_hi) of L (unknowns still to be updated)
+    const int ibase = blockIdx.x * 32 + warp * 4;
     for (int u = 0; u < 4; u += 2) {
         const int i0 = ibase + u, i1 = i0 + 1;
-        if (i0 >= c_hi) break;
+        if (i0 >= j0) break;
         const double* L0 = L + (size_t)i0 * lda + j0;
-        const double* L1 = (i1 < c_hi) ? L + (size_t)i1 * lda + j0 : L0;
+        const double* L1 = (i1 < j0) ? L + (size_t)i1 * lda + j0 : L0;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
         for (int c = lane; c < jb; c += 32) { a0 += L0[c] * ys[c]; a1 += L1[c] * ys[c]; }
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(256)
         a1 = warp_sum(a1);
         if (lane == 0) {
             rhs[i0] -= a0;
-            if (i1 < c_hi) rhs[i1] -= a1;
+            if (i1 < j0) rhs[i1] -= a1;
         }
     }
 }
@@ -811,65 +811,23 @@ void chol_build_tinv(const double* L, int n, int lda, CholWork& work, cudaStream
     work.tinv_for = L;
 }
 
-// One direction = n/256 dependent steps.  Step s: y_s = inv(L_ss) r_s (one CTA), then the remaining right-hand side is updated
-// with the 256-wide block column / row of L.  Only the NEXT block's 256 unknowns are on the critical path: they are updated by
-// a small launch on the main stream ("near", accumulated in x), everything behind them by a launch on the side stream ("far",
-// the HBM traffic, accumulated in a second vector z so that the two never write the same words).  r_s = x_s + z_s needs
-// near(s-1) (same stream) and far(<= s-2): the far update has a whole step of slack.
 static void chol_solve_enqueue(const double* L, int n, int lda, CholWork& work, double* x, double* tmp, int which, cudaStream_t st) {
     const int nstep = (int)cdiv(n, SW);
-    const bool split = nstep >= 8;
-    cudaStream_t sf = nullptr;
-    cudaEvent_t evY = nullptr, evF[2] = {nullptr, nullptr};
-    double* z = nullptr;
-    if (split) {
-        ensure_aux(work);
-        sf = work.aux; evY = work.ev[0]; evF[0] = work.ev[1]; evF[1] = work.ev[2];
-        if (work.zacc.n < (size_t)n) work.zacc.alloc((size_t)n);
-        z = work.zacc.p;
-    }
     for (int dir = 0; dir < 2; dir++) {
         if (!(which & (dir ? 2 : 1))) continue;
-        bool rec[2] = {false, false};                            // evF[k] holds a far update of this direction
-        if (split) {
-            LRN_CUDA(cudaMemsetAsync(z, 0, (size_t)n * sizeof(double), st));
-            LRN_CUDA(cudaEventRecord(evY, st));                  // the side stream must not run ahead of the clear of z
-            LRN_CUDA(cudaStreamWaitEvent(sf, evY, 0));
-        }
         for (int s = 0; s < nstep; s++) {
             const int b = dir ? nstep - 1 - s : s;
             const int j0 = b * SW, jb = (n - j0 < SW) ? (n - j0) : SW;
             const int bn = dir ? b - 1 : b + 1;
             const double* Xn = (bn >= 0 && bn < nstep && (size_t)(bn + 1) * SW * SW <= work.tinv.n) ? work.tinv.p + (size_t)bn * SW * SW : nullptr;
-            if (split && rec[s & 1]) LRN_CUDA(cudaStreamWaitEvent(st, evF[s & 1], 0));       // far(s-2) is complete
-            trsv_diag_kernel<<<1, 1024, 0, st>>>(work.tinv.p + (size_t)b * SW * SW, jb, x + j0, tmp + j0, dir, Xn, split ? z + j0 : nullptr);
+            trsv_diag_kernel<<<1, 1024, 0, st>>>(work.tinv.p + (size_t)b * SW * SW, jb, x + j0, tmp + j0, dir, Xn);
             LRN_CHECK_LAUNCH();
             const int rest = dir ? j0 : n - j0 - jb;
             if (rest <= 0) continue;
-            if (!split) {
-                if (!dir) trsv_update_fwd_kernel<<<(unsigned)cdiv(rest, 64), 256, 0, st>>>(L, lda, n, j0, jb, tmp + j0, x, j0 + jb);
-                else trsv_update_bwd_kernel<<<(unsigned)cdiv(rest, 32), 256, 0, st>>>(L, lda, j0, jb, tmp + j0, x, 0, j0);
-                LRN_CHECK_LAUNCH();
-                continue;
-            }
-            const int near = rest < SW ? rest : SW, far = rest - near;
-            rec[s & 1] = false;
-            if (far > 0) {
-                LRN_CUDA(cudaEventRecord(evY, st));
-                LRN_CUDA(cudaStreamWaitEvent(sf, evY, 0));
-                if (!dir) trsv_update_fwd_kernel<<<(unsigned)cdiv(far, 64), 256, 0, sf>>>(L, lda, n, j0, jb, tmp + j0, z, j0 + jb + near);
-                else trsv_update_bwd_kernel<<<(unsigned)cdiv(far, 32), 256, 0, sf>>>(L, lda, j0, jb, tmp + j0, z, 0, j0 - near);
-                LRN_CHECK_LAUNCH();
-                LRN_CUDA(cudaEventRecord(evF[s & 1], sf));
-                rec[s & 1] = true;
-            }
-            if (!dir) trsv_update_fwd_kernel<<<(unsigned)cdiv(near, 64), 256, 0, st>>>(L, lda, j0 + jb + near, j0, jb, tmp + j0, x, j0 + jb);
-            else trsv_update_bwd_kernel<<<(unsigned)cdiv(near, 32), 256, 0, st>>>(L, lda, j0, jb, tmp + j0, x, j0 - near, j0);
+            if (!dir) trsv_update_fwd_kernel<<<(unsigned)cdiv(rest, 64), 256, 0, st>>>(L, lda, n, j0, jb, tmp + j0, x);
+            else trsv_update_bwd_kernel<<<(unsigned)cdiv(rest, 32), 256, 0, st>>>(L, lda, j0, jb, tmp + j0, x);
             LRN_CHECK_LAUNCH();
         }
-        if (split)
-            for (int k = 0; k < 2; k++)
-                if (rec[k]) LRN_CUDA(cudaStreamWaitEvent(st, evF[k], 0));                    // join the side stream
         LRN_CUDA(cudaMemcpyAsync(x, tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
 }
