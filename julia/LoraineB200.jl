@@ -4,7 +4,8 @@
 #     using Loraine; include("LoraineB200.jl"); LoraineB200.enable!("/path/to/libloraine_b200.so"; ngpus = 1)
 #     model = Model(Loraine.Optimizer); ... ; optimize!(model)          # unchanged user code
 #
-# How it hooks in (no method of the reference is overwritten; every method below is MORE SPECIFIC than the reference's):
+# How it hooks in (no method of the reference is overwritten; every method below is MORE SPECIFIC than the reference's and falls
+# back to the reference's own method through `invoke` until `enable!` has been called):
 #   * `Solvers.setup_solver(::MySolver{Float64}, ::Halpha)`  runs the reference body (src/Solvers.jl:363-446) via `invoke`,
 #     then creates the device handle and uploads the prepared model (`attach!`);
 #   * `Solvers.initial_point(::MySolver{Float64})`           runs the reference body (src/initial_point.jl:1-81), then uploads
@@ -148,23 +149,27 @@ call0(solver, ::Val{:lrn_schur_factor}) = check(dev(solver), ccall((:lrn_schur_f
 # =====================================================================================================================
 function S.setup_solver(solver::S.MySolver{Float64}, halpha::S.Halpha)
     invoke(S.setup_solver, Tuple{S.MySolver,S.Halpha}, solver, halpha)      # the reference body: kit / datarank fall-backs, host zeros
+    ENABLED[] || return nothing                                             # not enabled: the reference's CPU path, untouched
     attach!(solver)
     return nothing
 end
 
 function S.initial_point(solver::S.MySolver{Float64})
     invoke(S.initial_point, Tuple{Any}, solver)                            # src/initial_point.jl:1-81 (a few norms of the model data)
+    ENABLED[] || return nothing
     upload_iterate!(solver)
     return nothing
 end
 
 function S.find_mu(solver::S.MySolver{Float64})                            # src/Solvers.jl:480-494
+    ENABLED[] || return invoke(S.find_mu, Tuple{Any}, solver)
     mu = Ref(0.0)
     check(dev(solver), ccall((:lrn_find_mu, LIB[]), Int32, (Ptr{Cvoid}, Ref{Float64}), dev(solver).h, mu), "lrn_find_mu")
     solver.mu = mu[]
 end
 
 function S.prepare_W(solver::S.MySolver{Float64})                          # src/prepare_W.jl:28-94
+    ENABLED[] || return invoke(S.prepare_W, Tuple{S.MySolver}, solver)
     st4 = Ref{Int32}(0)
     @timeit solver.to "prep W SVD" begin                                   # section name of src/prepare_W.jl:37
         check(dev(solver), ccall((:lrn_prepare_W, LIB[]), Int32, (Ptr{Cvoid}, Ref{Int32}), dev(solver).h, st4), "lrn_prepare_W")
@@ -183,6 +188,7 @@ function pcg(solver, kind)
 end
 
 function S.find_step(solver::S.MySolver{Float64})                          # src/predictor_corrector.jl:248-364
+    ENABLED[] || return invoke(S.find_step, Tuple{S.MySolver}, solver)
     d = dev(solver); md = solver.model
     a = zeros(max(1, md.nlmi)); b = zeros(max(1, md.nlmi)); al = Ref(1.0); bl = Ref(1.0)
     check(d, ccall((:lrn_find_step, LIB[]), Int32,
@@ -193,6 +199,7 @@ function S.find_step(solver::S.MySolver{Float64})                          # src
 end
 
 function S.predictor(solver::S.MySolver{Float64}, halpha::S.Halpha)        # src/predictor_corrector.jl:5-146, control flow kept
+    ENABLED[] || return invoke(S.predictor, Tuple{S.MySolver,S.Halpha}, solver, halpha)
     solver.predict = true
     call0(solver, Val(:lrn_residuals))                                     # :8-22
     if solver.kit == 0                                                     # :24-40 (section names of src/makeBBBB.jl:2,30)
@@ -245,6 +252,7 @@ function S.predictor(solver::S.MySolver{Float64}, halpha::S.Halpha)        # src
 end
 
 function S.sigma_update(solver::S.MySolver{Float64})                       # src/predictor_corrector.jl:148-179
+    ENABLED[] || return invoke(S.sigma_update, Tuple{S.MySolver}, solver)
     md = solver.model
     step_pred = min(minimum([solver.alpha; solver.alpha_lin]), minimum([solver.beta; solver.beta_lin]))
     expon_used = solver.mu > 1e-6 ? (step_pred < 1 / sqrt(3) ? 1.0 : max(solver.expon, 3 * step_pred^2)) :
@@ -261,6 +269,7 @@ function S.sigma_update(solver::S.MySolver{Float64})                       # src
 end
 
 function S.corrector(solver::S.MySolver{Float64}, halpha)                  # src/predictor_corrector.jl:181-246
+    ENABLED[] || return invoke(S.corrector, Tuple{Any,Any}, solver, halpha)
     solver.predict = false
     check(dev(solver), ccall((:lrn_rhs_corrector, LIB[]), Int32, (Ptr{Cvoid}, Float64, Float64), dev(solver).h,
                              Float64(solver.sigma), Float64(solver.mu)), "lrn_rhs_corrector")
@@ -275,6 +284,7 @@ function S.corrector(solver::S.MySolver{Float64}, halpha)                  # src
 end
 
 function S.myIPstep(solver::S.MySolver{Float64}, halpha::S.Halpha)         # src/Solvers.jl:448-478
+    ENABLED[] || return invoke(S.myIPstep, Tuple{S.MySolver,S.Halpha}, solver, halpha)
     solver.iter += 1
     if solver.iter > solver.maxit
         solver.status = 4
@@ -293,6 +303,7 @@ function S.myIPstep(solver::S.MySolver{Float64}, halpha::S.Halpha)         # src
 end
 
 function S.check_convergence(solver::S.MySolver{Float64})                  # src/Solvers.jl:496-568
+    ENABLED[] || return invoke(S.check_convergence, Tuple{Any}, solver)
     md = solver.model
     err = zeros(6); by = Ref(0.0); trCX = Ref(0.0); dx = Ref(0.0)
     check(dev(solver), ccall((:lrn_dimacs, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ref{Float64}, Ref{Float64}),
