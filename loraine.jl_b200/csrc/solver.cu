@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <thread>
 
 using namespace lrn;
 
@@ -358,6 +359,42 @@ double lambda_min(lrn_solver* h, const double* T, int m, int ld, double* lmax = 
     return r.lmin;
 }
 
+// lambda_min of two symmetric matrices at once (see the corrector branch of lrn_find_step)
+void lambda_min_pair(lrn_solver* h, const double* Ta, const double* Tb, int m, int ld, double* la, double* lb) {
+    Phase ph(h, LRN_T_EIGMIN);
+    const double tol = h->opt.lanczos_tol > 0 ? h->opt.lanczos_tol : 1e-8;
+    if (!h->st2) {
+        LRN_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+        LRN_CUDA(cudaEventCreateWithFlags(&h->ev2, cudaEventDisableTiming));
+    }
+    LRN_CUDA(cudaEventRecord(h->ev2, h->st));               // both matrices were produced on the main stream
+    LRN_CUDA(cudaStreamWaitEvent(h->st2, h->ev2, 0));
+    LanczosResult ra, rb;
+    std::string err_a;
+    const int dev = h->device, kmax = h->lanczos_kmax;
+    std::thread ta([&] {
+        try {
+            LRN_CUDA(cudaSetDevice(dev));
+            ra = lanczos_extreme(Ta, m, ld, 1, 0, nullptr, nullptr, 0, tol, h->lan2, h->st2, kmax);
+        } catch (const std::exception& e) { err_a = e.what(); }
+    });
+    try {
+        rb = lanczos_extreme(Tb, m, ld, 1, 0, nullptr, nullptr, 0, tol, h->lan, h->st, kmax);
+    } catch (...) { ta.join(); throw; }
+    ta.join();
+    if (!err_a.empty()) throw CudaError(err_a);
+    h->stat_lanczos_iters += ra.iters + rb.iters;
+    for (int k = 0; k < 2; k++) {                           // non-converged runs: guaranteed bounds instead of Ritz values
+        LanczosResult& r = k ? rb : ra;
+        if (r.converged) continue;
+        h->stat_lanczos_fail++;
+        const double sc = std::max(std::fabs(r.lmin), std::fabs(r.lmax));
+        if (r.resid_min > tol * (sc > 0 ? sc : 1.0)) r.lmin = extreme_by_bisection(h, k ? Tb : Ta, m, ld, 1.0, r.lmin);
+    }
+    *la = ra.lmin;
+    *lb = rb.lmin;
+}
+
 inline double steplen(double mimi, double tau) { return (mimi > -1e-6) ? 0.99 : std::min(1.0, -tau / mimi); }
 
 // Factor X (or S) of block `B` into L with the reference's try_cholesky retry loop (src/prepare_W.jl:5-26).
@@ -634,6 +671,8 @@ int32_t lrn_destroy(lrn_handle_t h) {
     for (auto& s_ : h->side) if (s_) { cudaStreamSynchronize(s_); cudaStreamDestroy(s_); }
     if (h->evFork) cudaEventDestroy(h->evFork);
     for (auto& e : h->evJoin) if (e) cudaEventDestroy(e);
+    if (h->st2) { cudaStreamSynchronize(h->st2); cudaStreamDestroy(h->st2); }
+    if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->nccl) { delete static_cast<DistCtx*>(h->nccl); h->nccl = nullptr; }
     delete h;
     if (st) cudaStreamDestroy(st);
@@ -1114,8 +1153,12 @@ int32_t lrn_find_step(lrn_handle_t h, int32_t predict, double sigma, double mu, 
                 beta[i] = steplen(lmin, tau);
                 alpha[i] = steplen(-1.0 - lmax, tau);
             } else if (!batched) {
-                alpha[i] = steplen(lambda_min(h, B.T4.p(), m, ld), tau);
-                beta[i] = steplen(lambda_min(h, B.T1.p(), m, ld), tau);
+                // corrector: the two smallest eigenvalues are independent Lanczos runs, each a chain of small latency-bound
+                // kernels with host check points: the X part runs on a second stream driven by a second host thread
+                double lx = 0.0, ls = 0.0;
+                lambda_min_pair(h, B.T4.p(), B.T1.p(), m, ld, &lx, &ls);
+                alpha[i] = steplen(lx, tau);
+                beta[i] = steplen(ls, tau);
             }
         }
         if (fan) side_join(h);

@@ -83,7 +83,9 @@ struct lrn_solver {
     lrn::DevBuf<int> eig_ms, eig_lds;
     lrn::DevBuf<double> eig_out;
     lrn::Reducer red;
-    lrn::LanczosWork lan;
+    lrn::LanczosWork lan, lan2;        // lan2 + st2: the second of two independent lambda_min runs (corrector) on its own stream
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev2 = nullptr;
     int lanczos_kmax = 500;            // Krylov dimension cap (test hook: small values force the bisection fallback)
     lrn::DMat eig_scratch;             // shifted copy of the matrix for the Cholesky bisection fallback of lambda_min
     lrn::CholWork eig_chol;
