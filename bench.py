@@ -438,6 +438,9 @@ def run_b200(args):
                                             if res["all_dmma"]["ms"] > 0 else None,
                                             launches=res["all_dmma"]["launches"], kernel_ms_per_step=res["all_dmma"]["ms"]),
                       by_kernel=fams,
+                      note="per-launch CUDA events on the launching stream; the panel stream and the main stream run this kernel "
+                           "concurrently during the factorisation (look-ahead), so launch durations overlap and share SMs: the sum "
+                           "understates the rate of the phase as a whole, which is schur.factor_tflops",
                       peak_source="measured in this run: register-resident mma.sync.m8n8k4.f64 loop on all SMs "
                                   "(MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.4 TFLOP/s)"),
         stats=res["stats"], dist_parity=parity,
