@@ -1,8 +1,8 @@
-// Blocked right-looking Cholesky with one-step look-ahead on two streams.  A panel's diagonal block (<= 512) is factored by
-// one cooperative kernel: 64x64 blocks are factored AND inverted in registers / shared memory, the full inverse of the
-// diagonal block is assembled, and the rows below are solved with ONE DMMA GEMM against it; the trailing update is a
-// lower-only SYRK-shaped product with K = panel width on the TMA-fed kernel.  Triangular solves advance 256 unknowns per
-// step through pre-built inverses of the 256x256 diagonal blocks (see chol_solve).
+// Blocked right-looking Cholesky with one-step look-ahead on two streams.  One cooperative launch per column panel
+// (panel_factor_kernel) factors the diagonal block -- 64 x 64 tiles factored AND inverted in registers -- and solves all rows
+// below it with DMMA tile products; the trailing update is a lower-only SYRK-shaped product with K = panel width on the TMA-fed
+// kernel (panels of 256 / 512 / 2 x 512 columns).  Triangular solves advance 256 unknowns per step through pre-built
+// inverses of the 256 x 256 diagonal blocks and are replayed as CUDA graphs (see chol_solve).
 #include "chol.cuh"
 #include "gemm.cuh"
 #include <cooperative_groups.h>
@@ -474,17 +474,6 @@ void potrf_small(double* A, int lda, int n, double* dinv, double* X, int ldx, in
     void* args[] = {&A, &lda, &n, &dinv, &X, &ldx, &info, &base};
     LRN_CUDA(cudaLaunchCooperativeKernel((void*)potrf_coop_kernel, dim3(G), dim3(256), args, POTRF_SMEM, st));
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-}
-
-__global__ void k_copy2d(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (i < rows && j < cols) dst[(size_t)j * ldd + i] = src[(size_t)j * lds + i];
-}
-void copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t st) {
-    if (rows <= 0 || cols <= 0) return;
-    dim3 grid((unsigned)cdiv(rows, 256), (unsigned)cols);
-    k_copy2d<<<grid, 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
-    LRN_CHECK_LAUNCH();
 }
 
 // Factor the kb x kb diagonal block at the top of a column panel AND solve the `rows_below` rows under it, in one cooperative

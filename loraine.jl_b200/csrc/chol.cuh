@@ -13,8 +13,6 @@ struct CholWork {
     DevBuf<double> dinv;      // cdiv(n,64) blocks of 64x64 (ld 64), zero above the diagonal
     DevBuf<int> info;         // [0] = 0 ok, >0 = 1-based index of the first non-positive pivot (LAPACK convention)
     int* info_ext = nullptr;  // optional external flag location (lets the caller gather many flags with one copy)
-    DevBuf<double> xinv;      // inverse of the current panel's diagonal block (kb x kb) + 64 x kb scratch
-    DevBuf<double> pout;      // out-of-place panel solve result (rows x kb)
     DevBuf<double> tinv, tscr; // inverses of the 256 x 256 diagonal blocks of L (triangular solves) + 64 x 64 scratch per block
     const double* tinv_for = nullptr;   // factor the inverses belong to (reset by every factorisation)
     // the launch sequence of a triangular solve (2 launches per 256 unknowns) only depends on (L, n, lda, x, tmp, which): it is
