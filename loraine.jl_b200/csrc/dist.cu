@@ -457,18 +457,34 @@ void cholesky_dist(double* A, int n, int lda, CholWork& work, DistCtx& ctx, int 
         LRN_CUDA(cudaEventRecord(evB, sp));
         LRN_CUDA(cudaStreamWaitEvent(st, evB, 0));
         if (p + 1 >= nblk) break;
-        // ---- trailing update with panel p on the main stream, two column blocks ahead first: column block p+1 (my rows are
-        //      solved next; its diagonal block was already updated on the diagonal stream), column block p+2 (its diagonal block
-        //      is factored during step p+1), then the rest
+        // ---- trailing update on the main stream.  Two column blocks ahead first: column block p+1 (my rows are solved next; its
+        //      diagonal block was already updated on the diagonal stream) and column block p+2 (its diagonal block is factored
+        //      during step p+1).  The REST of the trailing matrix is updated every second step only, with the two panels p-1, p at
+        //      once (K = 2 pw: half as many C-tile read-modify-write epilogues and pipeline fills per flop on the TMA-fed kernel):
+        //        even step p : columns p+1, p+2 with panel p                                         (rest deferred)
+        //        odd step p  : column p+1 with panel p, column p+2 with panels p-1..p, rest (>= p+3) with panels p-1..p
         const double* P = A + (size_t)c0 * lda;                            // column panel p: rows are global
         const int c1 = c0 + pw, c2 = std::min(n, c1 + pw), c3 = std::min(n, c2 + pw);
+        const bool pair_rest = (pw % 32 == 0);                             // (always: pw is 128, 256 or 512)
         mark(st, 10);
-        // (one launch for both look-ahead column blocks: N = 1024 keeps the strided-batch product on the TMA-fed kernel)
-        row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c1, c3, w, -1.0, 1.0, 0, true);
-        LRN_CUDA(cudaEventRecord(evU, st));
-        LRN_CUDA(cudaEventRecord(evU2, st));
-        mark(st, 11);
-        if (c3 < n) row_block_gemm(st, n, pw, rank, world, p + 3, P, lda, P, lda, A, lda, c3, n, w, -1.0, 1.0, 0, true);
+        if (!(p & 1) || !pair_rest) {
+            // (one launch for both look-ahead column blocks: N = 2 pw keeps the strided-batch product on the TMA-fed kernel)
+            row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c1, c3, w, -1.0, 1.0, 0, true);
+            LRN_CUDA(cudaEventRecord(evU, st));
+            LRN_CUDA(cudaEventRecord(evU2, st));
+            mark(st, 11);
+            const bool last_even_with_rest = pair_rest && (p + 2 >= nblk);   // no odd step follows that could take the rest
+            if ((!pair_rest || last_even_with_rest) && c3 < n)
+                row_block_gemm(st, n, pw, rank, world, p + 3, P, lda, P, lda, A, lda, c3, n, w, -1.0, 1.0, 0, true);
+        } else {
+            const double* P2 = P - (size_t)pw * lda;                       // panels p-1 and p side by side: K = 2 pw
+            row_block_gemm(st, n, pw, rank, world, p + 2, P, lda, P, lda, A, lda, c1, c2, w, -1.0, 1.0, 0, true);
+            LRN_CUDA(cudaEventRecord(evU, st));
+            if (c2 < n) row_block_gemm(st, n, pw, rank, world, p + 2, P2, lda, P2, lda, A, lda, c2, c3, pw + w, -1.0, 1.0, 0, true);
+            LRN_CUDA(cudaEventRecord(evU2, st));
+            mark(st, 11);
+            if (c3 < n) row_block_gemm(st, n, pw, rank, world, p + 3, P2, lda, P2, lda, A, lda, c3, n, pw + w, -1.0, 1.0, 0, true);
+        }
         mark(st, 12);
     }
     LRN_CUDA(cudaEventRecord(evD, sq));
