@@ -82,6 +82,29 @@ def lib():
         "lrn_dbg_gather_H": (i32, [vp]),
         "lrn_dist_unique_id": (i32, [C.c_char_p]),
         "lrn_dist_init": (i32, [vp, i32, i32, C.c_char_p]),
+        # include/loraine_b200_dd.h (double-double LP path)
+        "lrn_dd_create": (i32, [C.POINTER(vp), i64, i64, i32]),
+        "lrn_dd_set_lin": (i32, [vp, pi64, pi64, pdbl, pdbl, pdbl, pdbl]),
+        "lrn_dd_set_b": (i32, [vp, pdbl, pdbl]),
+        "lrn_dd_finalize": (i32, [vp]),
+        "lrn_dd_destroy": (i32, [vp]),
+        "lrn_dd_last_error": (C.c_char_p, [vp]),
+        "lrn_dd_set_iterate": (i32, [vp, pdbl, pdbl, pdbl, pdbl, pdbl, pdbl]),
+        "lrn_dd_get_solution": (i32, [vp, pdbl, pdbl, pdbl, pdbl, pdbl, pdbl]),
+        "lrn_dd_find_mu": (i32, [vp, pdbl]),
+        "lrn_dd_prepare_W": (i32, [vp]),
+        "lrn_dd_residuals": (i32, [vp]),
+        "lrn_dd_schur_assemble": (i32, [vp]),
+        "lrn_dd_rhs_predictor": (i32, [vp]),
+        "lrn_dd_rhs_corrector": (i32, [vp, pdbl, pdbl]),
+        "lrn_dd_schur_factor": (i32, [vp]),
+        "lrn_dd_schur_shift": (i32, [vp, dbl]),
+        "lrn_dd_schur_solve": (i32, [vp, i32]),
+        "lrn_dd_find_step": (i32, [vp, i32, pdbl, pdbl, dbl, pdbl, pdbl]),
+        "lrn_dd_sigma_trace": (i32, [vp, pdbl]),
+        "lrn_dd_dimacs": (i32, [vp, pdbl, pdbl, pdbl]),
+        "lrn_dd_get_array": (i32, [vp, i32, pdbl, pdbl]),
+        "lrn_dd_timers": (i32, [vp, pdbl, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -99,6 +122,12 @@ DECLARED_SYMBOLS = ["lrn_default_options", "lrn_create", "lrn_set_block_AA", "lr
                     "lrn_get_array", "lrn_apply_operator", "lrn_timers", "lrn_kernel_launches", "lrn_stats", "lrn_set_option",
                     "lrn_dist_unique_id", "lrn_dist_init", "lrn_create_multi",
                     "lrn_create_from_triplets", "lrn_load_sdpa", "lrn_initial_point", "lrn_get_dims", "lrn_timer_name"]
+
+DD_SYMBOLS = ["lrn_dd_create", "lrn_dd_set_lin", "lrn_dd_set_b", "lrn_dd_finalize", "lrn_dd_destroy", "lrn_dd_last_error",
+              "lrn_dd_set_iterate", "lrn_dd_get_solution", "lrn_dd_find_mu", "lrn_dd_prepare_W", "lrn_dd_residuals",
+              "lrn_dd_schur_assemble", "lrn_dd_rhs_predictor", "lrn_dd_rhs_corrector", "lrn_dd_schur_factor", "lrn_dd_schur_shift",
+              "lrn_dd_schur_solve", "lrn_dd_find_step", "lrn_dd_sigma_trace", "lrn_dd_dimacs", "lrn_dd_get_array", "lrn_dd_timers"]
+DD_ARR = dict(H=1, L=2, RP=3, RD=4, RHS=5, DELY=6, DELX=7, DELS=8, XN=9, SN=10, RNT=11, SI=12)
 
 DEBUG_SYMBOLS = ["lrn_dbg_gemm", "lrn_dbg_cholesky", "lrn_dbg_eig_small", "lrn_dbg_svd", "lrn_dbg_lanczos",
                  "lrn_dbg_batched_lambda_min", "lrn_dbg_peak", "lrn_dbg_gemm_profile", "lrn_dbg_set_shard", "lrn_dbg_compare",

@@ -585,11 +585,14 @@ def solve(s: MySolver, halpha: Halpha, max_iters=None, setup=True):
 
 class Optimizer:
     """Minimal stand-in for `Loraine.Optimizer{T}` (src/MOI_wrapper.jl:42-66, :86-103, :136-140, :241-354) so that tests and
-    the benchmark read like the reference's examples.  Only Float64 is accepted."""
+    the benchmark read like the reference's examples.  T = Float64, or "Float64x2" for models without PSD blocks (the
+    double-double LP path of dd_lp.py, examples/k.jl:8); every other element type is rejected -- there is no fallback."""
 
     def __init__(self, T=float):
-        if T not in (float, np.float64):
-            raise TypeError("Optimizer{T}: only T = Float64 is supported by the B200 path (no Float64xN fallback)")
+        self.dd = T == "Float64x2"
+        if not self.dd and T not in (float, np.float64):
+            raise TypeError("Optimizer{T}: only T = Float64 (and Float64x2 for models without PSD blocks) is supported by "
+                            "the B200 path (no Float64xN fallback)")
         self.options = dict(DEFAULT_OPTIONS)
         self.solver = None
         self.halpha = None
@@ -610,6 +613,10 @@ class Optimizer:
         opts = dict(self.options)
         if self.silent:
             opts["verb"] = 0
+        if self.dd:
+            from . import dd_lp
+            self.solver, self.halpha = dd_lp.DDSolver(model, opts), None       # raises TypeError when the model has PSD blocks
+            return
         self.solver, self.halpha = load(model, opts)
 
     def load_sdpa(self, n, bs, c, body, max_sense=False):
@@ -619,11 +626,22 @@ class Optimizer:
         self.solver.sdpa_arrays = (int(n), [int(b) for b in bs], np.asarray(c, float), np.asarray(body, float))
 
     def optimize(self, max_iters=None):
+        if self.dd:
+            from . import dd_lp
+            dd_lp.solve(self.solver, max_iters=max_iters)
+            return
         solve(self.solver, self.halpha, max_iters=max_iters)
 
     def objective_value(self):
         s = self.solver
         val = float(s.model.b @ s.y) - s.model.b_const
+        return val if self.max_sense else -val
+
+    def objective_value_dd(self):
+        """Float64x2 solves: the objective as an exact fraction of the (hi, lo) result (b'y - b_const, sense applied)."""
+        from . import dd_lp
+        s = self.solver
+        val = dd_lp.frac(s.by) - dd_lp.Fraction(s.model.b_const)
         return val if self.max_sense else -val
 
     def dual_objective_value(self):

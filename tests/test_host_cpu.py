@@ -21,11 +21,12 @@ def _declared(header):
 def test_library_exports_every_declared_symbol(pkg):
     from loraine_jl_b200 import _lib
     L = C.CDLL(_lib.LIB_PATH)
-    names = _declared("loraine_b200.h") + _declared("loraine_b200_debug.h")
-    assert len(names) >= 40
+    names = _declared("loraine_b200.h") + _declared("loraine_b200_debug.h") + _declared("loraine_b200_dd.h")
+    assert len(names) >= 60
     for n in names:
         assert hasattr(L, n), n
     assert set(_lib.DECLARED_SYMBOLS) <= set(names)
+    assert set(_lib.DD_SYMBOLS) == set(_declared("loraine_b200_dd.h"))
 
 
 def test_timer_names_follow_the_reference_sections(pkg):
@@ -56,7 +57,11 @@ def test_non_float64_is_rejected(pkg):
     with pytest.raises(TypeError):
         pkg.Optimizer(T=np.float32)
     with pytest.raises(TypeError):
-        pkg.Optimizer(T="Float64x2")
+        pkg.Optimizer(T="Float64x3")
+    # Float64x2 exists for models WITHOUT PSD blocks only (double-double LP path); a semidefinite model is rejected
+    opt = pkg.Optimizer(T="Float64x2")
+    with pytest.raises(TypeError):
+        opt.copy_to(pkg.RawProblem(**je.fields(je.ex_corr("Max"))))
     md = pkg.prepare_model(pkg.RawProblem(**je.fields(je.ex_k_lp())))
     with pytest.raises(TypeError):
         pkg.load(md, dict(verb=0), T=np.longdouble)
