@@ -25,7 +25,7 @@ struct lrn_dd_solver {
     DevBuf<int> cptr, cidx, rptr, ridx;
     DevBuf<dd> cval, rval;
     DevBuf<dd> d, b, x, s, si, y, rp, rd, rhs, dely, dx, ds, xn, sn, rnt, w, tl, tn;
-    DevBuf<dd> H, L, red;
+    DevBuf<dd> H, L, red, rdiag;
     DevBuf<int> info;
     bool have_lin = false, have_b = false, finalized = false, have_iterate = false, have_H = false, have_factor = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -89,8 +89,12 @@ __global__ void k_dd_shift_diag(int n, dd* __restrict__ H, double delta) {
 // ------------------------------------------------------------------------------------------------------------------------
 // tiled right-looking Cholesky (32 x 32 tiles): factor the diagonal tile, solve the tiles below it, update the trailing tiles
 // ------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TS * TS) k_dd_potrf_tile(dd* __restrict__ A, int n, int k0, int w, int* __restrict__ info) {
+// (the reciprocals of the pivots go to rdiag: the solves below multiply by them instead of dividing -- a double-double division
+// is ~10 times a multiplication)
+__global__ void __launch_bounds__(TS * TS) k_dd_potrf_tile(dd* __restrict__ A, int n, int k0, int w, int* __restrict__ info,
+                                                           dd* __restrict__ rdiag) {
     __shared__ dd t[TS][TS + 1];
+    __shared__ dd rinv[TS];
     __shared__ int bad;
     const int r = threadIdx.x, c = threadIdx.y;           // r fastest: coalesced along a column
     if (r == 0 && c == 0) bad = 0;
@@ -100,14 +104,18 @@ __global__ void __launch_bounds__(TS * TS) k_dd_potrf_tile(dd* __restrict__ A, i
     for (int j = 0; j < w; j++) {
         if (r == j && c == j) {
             if (dd_le_zero(t[j][j]) || !(t[j][j].hi == t[j][j].hi)) bad = 1;
-            else t[j][j] = dd_sqrt(t[j][j]);
+            else {
+                t[j][j] = dd_sqrt(t[j][j]);
+                rinv[j] = dd_recip(t[j][j]);
+                rdiag[k0 + j] = rinv[j];
+            }
         }
         __syncthreads();
         if (bad) {
             if (r == 0 && c == 0) *info = k0 + j + 1;
             return;
         }
-        if (c == j && r > j && r < w) t[r][j] = dd_div(t[r][j], t[j][j]);
+        if (c == j && r > j && r < w) t[r][j] = dd_mul(t[r][j], rinv[j]);
         __syncthreads();
         if (c > j && c < w && r >= c && r < w) t[r][c] = dd_fms(t[r][j], t[c][j], t[r][c]);
         __syncthreads();
@@ -116,10 +124,12 @@ __global__ void __launch_bounds__(TS * TS) k_dd_potrf_tile(dd* __restrict__ A, i
 }
 
 // X Lkk' = A for the 32-row tile `blockIdx.x` below the diagonal tile: one warp, lane = row of the tile
-__global__ void __launch_bounds__(TS) k_dd_trsm_tile(dd* __restrict__ A, int n, int k0, int w) {
+__global__ void __launch_bounds__(TS) k_dd_trsm_tile(dd* __restrict__ A, int n, int k0, int w, const dd* __restrict__ rdiag) {
     __shared__ dd l[TS][TS + 1];
     __shared__ dd xr[TS][TS + 1];
+    __shared__ dd rd[TS];
     const int lane = threadIdx.x;
+    if (lane < w) rd[lane] = rdiag[k0 + lane];
     const int i0 = k0 + w + blockIdx.x * TS, row = i0 + lane;
     for (int c = 0; c < w; c++) {
         if (lane < w) l[lane][c] = A[(size_t)(k0 + c) * n + k0 + lane];
@@ -128,9 +138,18 @@ __global__ void __launch_bounds__(TS) k_dd_trsm_tile(dd* __restrict__ A, int n, 
     __syncwarp();
     if (row < n) {
         for (int c = 0; c < w; c++) {
-            dd v = xr[lane][c];
-            for (int p = 0; p < c; p++) v = dd_fms(xr[lane][p], l[c][p], v);
-            xr[lane][c] = dd_div(v, l[c][c]);
+            // four independent partial sums: a double-double multiply-add is a ~25-deep dependent chain
+            dd a0 = xr[lane][c], a1 = dd_make(0.0), a2 = dd_make(0.0), a3 = dd_make(0.0);
+            int p = 0;
+            for (; p + 4 <= c; p += 4) {
+                a0 = dd_fms(xr[lane][p], l[c][p], a0);
+                a1 = dd_fms(xr[lane][p + 1], l[c][p + 1], a1);
+                a2 = dd_fms(xr[lane][p + 2], l[c][p + 2], a2);
+                a3 = dd_fms(xr[lane][p + 3], l[c][p + 3], a3);
+            }
+            for (; p < c; p++) a0 = dd_fms(xr[lane][p], l[c][p], a0);
+            const dd v = dd_add(dd_add(a0, a1), dd_add(a2, a3));
+            xr[lane][c] = dd_mul(v, rd[c]);
         }
         for (int c = 0; c < w; c++) A[(size_t)(k0 + c) * n + row] = xr[lane][c];
     }
@@ -160,7 +179,7 @@ __global__ void __launch_bounds__(TS * TS) k_dd_syrk_tile(dd* __restrict__ A, in
 // ------------------------------------------------------------------------------------------------------------------------
 // triangular solves with the dd factor: one CTA of 1024 threads, 32 unknowns per step
 // ------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_dd_trsv_fwd(const dd* __restrict__ L, int n, dd* __restrict__ x) {
+__global__ void __launch_bounds__(1024) k_dd_trsv_fwd(const dd* __restrict__ L, const dd* __restrict__ rdiag, int n, dd* __restrict__ x) {
     __shared__ dd xt[TS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k0 = 0; k0 < n; k0 += TS) {
@@ -169,7 +188,7 @@ __global__ void __launch_bounds__(1024) k_dd_trsv_fwd(const dd* __restrict__ L, 
             dd v = (lane < w) ? x[k0 + lane] : dd_make(0.0);
             for (int c = 0; c < w; c++) {
                 dd xc = dd_make(0.0);
-                if (lane == c) xc = dd_div(v, L[(size_t)(k0 + c) * n + k0 + c]);
+                if (lane == c) xc = dd_mul(v, rdiag[k0 + c]);
                 xc = dd_shfl(xc, c);
                 if (lane == c) v = xc;
                 else if (lane > c && lane < w) v = dd_fms(L[(size_t)(k0 + c) * n + k0 + lane], xc, v);
@@ -178,15 +197,22 @@ __global__ void __launch_bounds__(1024) k_dd_trsv_fwd(const dd* __restrict__ L, 
         }
         __syncthreads();
         for (int i = k0 + w + tid; i < n; i += blockDim.x) {
-            dd v = x[i];
-            for (int c = 0; c < w; c++) v = dd_fms(L[(size_t)(k0 + c) * n + i], xt[c], v);
-            x[i] = v;
+            dd a0 = x[i], a1 = dd_make(0.0), a2 = dd_make(0.0), a3 = dd_make(0.0);
+            int c = 0;
+            for (; c + 4 <= w; c += 4) {
+                a0 = dd_fms(L[(size_t)(k0 + c) * n + i], xt[c], a0);
+                a1 = dd_fms(L[(size_t)(k0 + c + 1) * n + i], xt[c + 1], a1);
+                a2 = dd_fms(L[(size_t)(k0 + c + 2) * n + i], xt[c + 2], a2);
+                a3 = dd_fms(L[(size_t)(k0 + c + 3) * n + i], xt[c + 3], a3);
+            }
+            for (; c < w; c++) a0 = dd_fms(L[(size_t)(k0 + c) * n + i], xt[c], a0);
+            x[i] = dd_add(dd_add(a0, a1), dd_add(a2, a3));
         }
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(1024) k_dd_trsv_bwd(const dd* __restrict__ L, int n, dd* __restrict__ x) {
+__global__ void __launch_bounds__(1024) k_dd_trsv_bwd(const dd* __restrict__ L, const dd* __restrict__ rdiag, int n, dd* __restrict__ x) {
     __shared__ dd tsum[TS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int last = ((n - 1) / TS) * TS;
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(1024) k_dd_trsv_bwd(const dd* __restrict__ L, 
             dd v = (lane < w) ? dd_sub(x[k0 + lane], tsum[lane]) : dd_make(0.0);
             for (int c = w - 1; c >= 0; c--) {
                 dd xc = dd_make(0.0);
-                if (lane == c) xc = dd_div(v, L[(size_t)(k0 + c) * n + k0 + c]);
+                if (lane == c) xc = dd_mul(v, rdiag[k0 + c]);
                 xc = dd_shfl(xc, c);
                 if (lane == c) v = xc;
                 else if (lane < c) v = dd_fms(L[(size_t)(k0 + lane) * n + k0 + c], xc, v);    // L'[lane, c] = L[c, lane]
@@ -417,8 +443,8 @@ void dot(lrn_dd_solver* h, int n, const dd* a, const dd* b, int slot) {
     LRN_CHECK_LAUNCH();
 }
 void trsv(lrn_dd_solver* h, bool fwd, dd* x) {
-    if (fwd) k_dd_trsv_fwd<<<1, 1024, 0, h->st>>>(h->L.p, h->n, x);
-    else k_dd_trsv_bwd<<<1, 1024, 0, h->st>>>(h->L.p, h->n, x);
+    if (fwd) k_dd_trsv_fwd<<<1, 1024, 0, h->st>>>(h->L.p, h->rdiag.p, h->n, x);
+    else k_dd_trsv_bwd<<<1, 1024, 0, h->st>>>(h->L.p, h->rdiag.p, h->n, x);
     LRN_CHECK_LAUNCH();
 }
 
@@ -446,7 +472,7 @@ int32_t lrn_dd_create(lrn_dd_handle_t* out, int64_t n_var, int64_t nlin, int32_t
         h->nlin = (int)nlin;
         const size_t n = (size_t)n_var, m = (size_t)nlin;
         for (DevBuf<dd>* v : {&h->d, &h->x, &h->s, &h->si, &h->rd, &h->dx, &h->ds, &h->xn, &h->sn, &h->rnt, &h->w, &h->tl}) v->alloc(m);
-        for (DevBuf<dd>* v : {&h->b, &h->y, &h->rp, &h->rhs, &h->dely, &h->tn}) v->alloc(n);
+        for (DevBuf<dd>* v : {&h->b, &h->y, &h->rp, &h->rhs, &h->dely, &h->tn, &h->rdiag}) v->alloc(n);
         h->H.alloc(n * n);
         h->L.alloc(n * n);
         h->red.alloc(R_COUNT);
@@ -633,12 +659,12 @@ int32_t lrn_dd_schur_factor(lrn_dd_handle_t h) {
             LRN_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
             for (int k0 = 0; k0 < n; k0 += TS) {
                 const int w = std::min(TS, n - k0);
-                k_dd_potrf_tile<<<1, dim3(TS, TS), 0, h->st>>>(h->L.p, n, k0, w, h->info.p);
+                k_dd_potrf_tile<<<1, dim3(TS, TS), 0, h->st>>>(h->L.p, n, k0, w, h->info.p, h->rdiag.p);
                 LRN_CHECK_LAUNCH();
                 const int below = n - k0 - w;
                 if (below <= 0) break;
                 const unsigned nt = (unsigned)cdiv(below, TS);
-                k_dd_trsm_tile<<<nt, TS, 0, h->st>>>(h->L.p, n, k0, w);
+                k_dd_trsm_tile<<<nt, TS, 0, h->st>>>(h->L.p, n, k0, w, h->rdiag.p);
                 LRN_CHECK_LAUNCH();
                 k_dd_syrk_tile<<<dim3(nt, nt), dim3(TS, TS), 0, h->st>>>(h->L.p, n, k0, w);
                 LRN_CHECK_LAUNCH();
