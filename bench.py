@@ -465,6 +465,7 @@ def run_b200(args):
                            stats=m["stats"])
             r.s.close()
             del r
+        subs["dd_lp"] = dd_lp_record(pkg, sub_args)
         line["sub_records"] = subs
     if world == 1 and not args.no_cpu_baseline:
         raw, note, cores, phases = cpu_iterations(pkg, args.workload, 0, 1)
@@ -474,6 +475,51 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def dd_lp_record(pkg, args):
+    """Double-double (Float64x2) LP path (include/loraine_b200_dd.h): sec / IP iteration on a synthetic LP with
+    2000 multipliers and 5000 LP rows (2 % dense), the rate of the double-double Cholesky against the FP64 issue bound, and a full
+    solve to DIMACS error 1e-24."""
+    import time
+    import torch
+    from loraine_jl_b200 import dd_lp
+    n, nlin = 2000, 5000
+    spec = pkg.problems.random_lp(n, nlin, 1, density=0.02)
+    md = pkg.prepare_model(pkg.RawProblem(**spec))
+    s = dd_lp.DDSolver(md, dict(pkg.DEFAULT_OPTIONS, eDIMACS=1e-24, verb=0))
+    dd_lp.setup_solver(s)
+    dd_lp.initial_point(s)
+    for _ in range(3):                                     # warm-up iterations (the iterate stays well inside the cone)
+        dd_lp.myIPstep(s)
+    s.timers(reset=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dd_lp.myIPstep(s)
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / args.steps
+    t = s.timers()
+    s.itertime = 0.0
+    dd_lp.check_convergence(s)
+    t1 = time.perf_counter()
+    dd_lp.solve(s, setup=False)
+    solve_s = time.perf_counter() - t1
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    clk = torch.cuda.clock_rate() * 1e6 if hasattr(torch.cuda, "clock_rate") else 1.965e9
+    # one double-double multiply-add = 29 FP64 instructions (9 product + 20 accurate sum); 64 FP64 instructions / clk / SM
+    bound = 64.0 * sm * 1.965e9 / 29.0
+    fma = n ** 3 / 3.0
+    rate = fma / (t["schur_factor"] / args.steps * 1e-3)
+    rec = dict(workload="synthetic LP without PSD blocks, Optimizer{Float64x2}: 2000 multipliers, 5000 LP rows, 2 % dense",
+               value=sec, unit=UNIT, steps=args.steps, warmup=3, dtype="f64x2 (double-double)",
+               phases_ms_per_iteration={k: v / args.steps for k, v in t.items()},
+               cholesky=dict(dd_fma_per_s=rate, bound_dd_fma_per_s=bound, frac=rate / bound,
+                             note="n^3/3 double-double multiply-adds; bound = FP64 issue rate (64 / clk / SM at 1965 MHz) / 29 "
+                                  "instructions per double-double multiply-add"),
+               solve=dict(status=int(s.status), iterations=int(s.iter), dimacs_error=float(s.DIMACS_error), seconds_after_warmup=solve_s))
+    s.close()
+    return rec
 
 
 if __name__ == "__main__":

@@ -7,6 +7,7 @@ with `model.write_sdpa` -- the Julia reference.
 from __future__ import annotations
 
 import numpy as np
+import scipy.sparse as sp
 
 
 def _torus_edges(rows, cols):
@@ -126,6 +127,23 @@ def large_schur(m=1000, n=40000, seed=40000):
             c[k] = float(np.sum(V * Xs[np.ix_(idx, idx)]))
     body.append(np.column_stack([ks, np.ones(len(ks)), ii, jj, vv]))
     return n, [m], c, np.concatenate(body)
+
+
+
+def random_lp(n, nlin, seed, density=0.5):
+    """Strictly feasible primal-dual LP pair in the reference's LP-block form (src/predictor_corrector.jl:19-20):
+    C x = b, x >= 0 and C' y + s = d, s >= 0 (no PSD block).  Returns the RawProblem fields."""
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, nlin)) * (rng.random((n, nlin)) < density)
+    for i in range(n):                                   # no empty row / column
+        M[i, rng.integers(nlin)] += 1.0 + rng.random()
+    for k in range(nlin):
+        if not M[:, k].any():
+            M[rng.integers(n), k] = 1.0
+    xs = 0.5 + rng.random(nlin)
+    ys = rng.standard_normal(n)
+    ss = 0.5 + rng.random(nlin)
+    return dict(n=n, msizes=[], A=[], b=M @ xs, b_const=0.0, C_lin=sp.csc_matrix(M), d_lin=M.T @ ys + ss)
 
 
 CONFIGS = {
