@@ -26,7 +26,8 @@ struct lrn_dd_solver {
     DevBuf<dd> cval, rval;
     DevBuf<dd> d, b, x, s, si, y, rp, rd, rhs, dely, dx, ds, xn, sn, rnt, w, tl, tn;
     DevBuf<dd> H, L, red, rdiag;
-    DevBuf<int> info;
+    DevBuf<int> info, flags;      // info[0]: Cholesky pivot, info[1]: time-out of the flag wait in the multi-CTA solves
+    int trsv_ctas = 0, trsv_epoch = 0;
     bool have_lin = false, have_b = false, finalized = false, have_iterate = false, have_H = false, have_factor = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double t_ms[4] = {0, 0, 0, 0};
@@ -242,6 +243,110 @@ __global__ void __launch_bounds__(1024) k_dd_trsv_bwd(const dd* __restrict__ L, 
     }
 }
 
+// Multi-CTA variant for more than two tiles: row tile i (32 unknowns) belongs to CTA i mod G (backward: counted from the end);
+// a CTA subtracts the products with the finished tiles as they are published (flag word per tile, value = epoch of this
+// launch), then solves its diagonal tile and publishes.  The factor is streamed by all CTAs instead of one SM (the single-CTA
+// kernel is bound by what one SM can pull from HBM).  Launched cooperatively: the wait needs every CTA resident.
+constexpr int TRSV_T = 256;                // 8 warps
+constexpr long long TRSV_SPIN_MAX = 1ll << 26;
+
+__device__ __forceinline__ bool dd_wait_flag(const int* flag, int epoch, int* err) {
+    long long spins = 0;
+    while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) return true;
+        if (++spins > TRSV_SPIN_MAX || *(volatile int*)err != 0) { *(volatile int*)err = 1; return false; }
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ dd dd_ldcg(const dd* p) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return dd_make(v.x, v.y);
+}
+
+__global__ void __launch_bounds__(TRSV_T) k_dd_trsv_multi(const dd* __restrict__ L, const dd* __restrict__ rdiag, int n, dd* x,
+                                                         int* flags, int epoch, int backward, int* err) {
+    __shared__ dd part[TRSV_T / 32][TS];
+    __shared__ int failed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = TRSV_T / 32;
+    const int nt = (n + TS - 1) / TS, G = gridDim.x;
+    if (tid == 0) failed = 0;
+    __syncthreads();
+    for (int seq = blockIdx.x; seq < nt; seq += G) {
+        const int i = backward ? nt - 1 - seq : seq;
+        const int r0 = i * TS, w = min(TS, n - r0);
+        // ---- products with the tiles this one depends on: forward k < i (lane = row of tile i), backward k > i (lane = column) ----
+        dd a0 = dd_make(0.0), a1 = dd_make(0.0), a2 = dd_make(0.0), a3 = dd_make(0.0);
+        const int ndep = backward ? nt - 1 - i : i;
+        for (int q = warp; q < ndep; q += nw) {
+            const int k = backward ? nt - 1 - q : q;           // dependencies in the order they are published
+            bool ok = true;
+            if (lane == 0) ok = dd_wait_flag(flags + k, epoch, err);
+            ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+            if (!ok) { failed = 1; break; }
+            const int c0 = k * TS, wk = min(TS, n - c0);
+            if (lane < w) {
+                if (!backward) {
+                    const dd* Lp = L + (size_t)c0 * n + r0 + lane;             // L[r0 + lane, c0 + c]
+                    int c = 0;
+                    for (; c + 4 <= wk; c += 4) {
+                        a0 = dd_fma(Lp[(size_t)c * n], dd_ldcg(x + c0 + c), a0);
+                        a1 = dd_fma(Lp[(size_t)(c + 1) * n], dd_ldcg(x + c0 + c + 1), a1);
+                        a2 = dd_fma(Lp[(size_t)(c + 2) * n], dd_ldcg(x + c0 + c + 2), a2);
+                        a3 = dd_fma(Lp[(size_t)(c + 3) * n], dd_ldcg(x + c0 + c + 3), a3);
+                    }
+                    for (; c < wk; c++) a0 = dd_fma(Lp[(size_t)c * n], dd_ldcg(x + c0 + c), a0);
+                } else {
+                    const dd* Lp = L + (size_t)(r0 + lane) * n + c0;           // L'[r0 + lane, c0 + c] = L[c0 + c, r0 + lane]
+                    int c = 0;
+                    for (; c + 4 <= wk; c += 4) {
+                        a0 = dd_fma(Lp[c], dd_ldcg(x + c0 + c), a0);
+                        a1 = dd_fma(Lp[c + 1], dd_ldcg(x + c0 + c + 1), a1);
+                        a2 = dd_fma(Lp[c + 2], dd_ldcg(x + c0 + c + 2), a2);
+                        a3 = dd_fma(Lp[c + 3], dd_ldcg(x + c0 + c + 3), a3);
+                    }
+                    for (; c < wk; c++) a0 = dd_fma(Lp[c], dd_ldcg(x + c0 + c), a0);
+                }
+            }
+        }
+        part[warp][lane] = dd_add(dd_add(a0, a1), dd_add(a2, a3));
+        __syncthreads();
+        if (failed) return;                                     // time-out: reported through *err by the host
+        // ---- diagonal tile: warp 0 ----
+        if (warp == 0) {
+            dd v = dd_make(0.0);
+            if (lane < w) {
+                dd sum = part[0][lane];
+                for (int q = 1; q < nw; q++) sum = dd_add(sum, part[q][lane]);
+                v = dd_sub(x[r0 + lane], sum);
+            }
+            if (!backward) {
+                for (int c = 0; c < w; c++) {
+                    dd xc = dd_make(0.0);
+                    if (lane == c) xc = dd_mul(v, rdiag[r0 + c]);
+                    xc = dd_shfl(xc, c);
+                    if (lane == c) v = xc;
+                    else if (lane > c && lane < w) v = dd_fms(L[(size_t)(r0 + c) * n + r0 + lane], xc, v);
+                }
+            } else {
+                for (int c = w - 1; c >= 0; c--) {
+                    dd xc = dd_make(0.0);
+                    if (lane == c) xc = dd_mul(v, rdiag[r0 + c]);
+                    xc = dd_shfl(xc, c);
+                    if (lane == c) v = xc;
+                    else if (lane < c) v = dd_fms(L[(size_t)(r0 + lane) * n + r0 + c], xc, v);
+                }
+            }
+            if (lane < w) x[r0 + lane] = v;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + i), "r"(epoch) : "memory");
+        }
+        __syncthreads();                                        // part[] is reused by the next tile of this CTA
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // element-wise kernels
 // ------------------------------------------------------------------------------------------------------------------------
@@ -443,6 +548,19 @@ void dot(lrn_dd_solver* h, int n, const dd* a, const dd* b, int slot) {
     LRN_CHECK_LAUNCH();
 }
 void trsv(lrn_dd_solver* h, bool fwd, dd* x) {
+    const int nt = (int)cdiv(h->n, TS);
+    if (nt > 2 && h->trsv_ctas > 0) {
+        const dd* Lp = h->L.p;
+        const dd* rd = h->rdiag.p;
+        int n = h->n, epoch = ++h->trsv_epoch, backward = fwd ? 0 : 1;
+        int* flags = h->flags.p;
+        int* err = h->info.p + 1;
+        void* args[] = {&Lp, &rd, &n, &x, &flags, &epoch, &backward, &err};
+        LRN_CUDA(cudaLaunchCooperativeKernel((const void*)k_dd_trsv_multi, dim3((unsigned)std::min(nt, h->trsv_ctas)), dim3(TRSV_T),
+                                             args, 0, h->st));
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        return;
+    }
     if (fwd) k_dd_trsv_fwd<<<1, 1024, 0, h->st>>>(h->L.p, h->rdiag.p, h->n, x);
     else k_dd_trsv_bwd<<<1, 1024, 0, h->st>>>(h->L.p, h->rdiag.p, h->n, x);
     LRN_CHECK_LAUNCH();
@@ -476,7 +594,13 @@ int32_t lrn_dd_create(lrn_dd_handle_t* out, int64_t n_var, int64_t nlin, int32_t
         h->H.alloc(n * n);
         h->L.alloc(n * n);
         h->red.alloc(R_COUNT);
-        h->info.alloc(1);
+        h->info.alloc(2);
+        h->flags.alloc((size_t)cdiv(n_var, TS));
+        // every CTA of the multi-CTA triangular solve must be resident (it waits on flags published by the others)
+        int per_sm = 0, coop = 0;
+        LRN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+        LRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dd_trsv_multi, TRSV_T, 0));
+        h->trsv_ctas = (coop && per_sm > 0) ? std::min(prop.multiProcessorCount, 128) : 0;
         return LRN_OK;
     });
     if (rc != LRN_OK) {
@@ -710,6 +834,13 @@ int32_t lrn_dd_schur_solve(lrn_dd_handle_t h, int32_t which) {
         for (int rep = 0; rep < (which == 6 ? 2 : 1); rep++) {
             trsv(h, true, h->dely.p);
             trsv(h, false, h->dely.p);
+        }
+        int timed_out = 0;
+        LRN_CUDA(cudaMemcpyAsync(&timed_out, h->info.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        LRN_CUDA(cudaStreamSynchronize(h->st));
+        if (timed_out) {
+            LRN_CUDA(cudaMemsetAsync(h->info.p + 1, 0, sizeof(int), h->st));
+            throw std::runtime_error("double-double triangular solve: flag wait timed out");
         }
         return LRN_OK;
     });
