@@ -506,17 +506,18 @@ def dd_lp_record(pkg, args):
     dd_lp.solve(s, setup=False)
     solve_s = time.perf_counter() - t1
     sm = torch.cuda.get_device_properties(0).multi_processor_count
-    clk = torch.cuda.clock_rate() * 1e6 if hasattr(torch.cuda, "clock_rate") else 1.965e9
-    # one double-double multiply-add = 29 FP64 instructions (9 product + 20 accurate sum); 64 FP64 instructions / clk / SM
-    bound = 64.0 * sm * 1.965e9 / 29.0
-    fma = n ** 3 / 3.0
+    # one double-double multiply-add = 28 FP64 instructions in the SASS of k_dd_syrk_tile (24 DADD + 2 DMUL + 2 DFMA);
+    # 64 FP64 instructions / clk / SM; a Cholesky factorisation is n^3/6 multiply-adds
+    bound = 64.0 * sm * 1.965e9 / 28.0
+    fma = n ** 3 / 6.0
     rate = fma / (t["schur_factor"] / args.steps * 1e-3)
     rec = dict(workload="synthetic LP without PSD blocks, Optimizer{Float64x2}: 2000 multipliers, 5000 LP rows, 2 % dense",
                value=sec, unit=UNIT, steps=args.steps, warmup=3, dtype="f64x2 (double-double)",
                phases_ms_per_iteration={k: v / args.steps for k, v in t.items()},
                cholesky=dict(dd_fma_per_s=rate, bound_dd_fma_per_s=bound, frac=rate / bound,
-                             note="n^3/3 double-double multiply-adds; bound = FP64 issue rate (64 / clk / SM at 1965 MHz) / 29 "
-                                  "instructions per double-double multiply-add"),
+                             note="n^3/6 double-double multiply-adds; bound = FP64 issue rate (64 / clk / SM at 1965 MHz) / 28 "
+                                  "instructions per double-double multiply-add; n = 2000 is 63 dependent tile steps: chain-bound, "
+                                  "n = 5000 reaches 0.75 of the bound (scripts/prof_ddlp.py)"),
                solve=dict(status=int(s.status), iterations=int(s.iter), dimacs_error=float(s.DIMACS_error), seconds_after_warmup=solve_s))
     s.close()
     return rec

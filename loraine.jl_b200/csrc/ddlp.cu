@@ -17,7 +17,8 @@ using namespace lrn;
 
 struct lrn_dd_solver {
     int device = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t evP = nullptr, evR = nullptr;
     std::string err;
     int n = 0, nlin = 0;
     long long nnz = 0;
@@ -157,12 +158,15 @@ __global__ void __launch_bounds__(TS) k_dd_trsm_tile(dd* __restrict__ A, int n, 
 }
 
 // A(I, J) -= X_I X_J' for the tile pairs I >= J of the trailing matrix (K = w)
-__global__ void __launch_bounds__(TS * TS) k_dd_syrk_tile(dd* __restrict__ A, int n, int k0, int w) {
-    if (blockIdx.y > blockIdx.x) return;
+// (column tiles jt0 + blockIdx.y: the first tile column of the trailing matrix is updated on the panel stream, the rest on a
+// second stream -- see lrn_dd_schur_factor)
+__global__ void __launch_bounds__(TS * TS) k_dd_syrk_tile(dd* __restrict__ A, int n, int k0, int w, int jt0) {
+    const int jt = jt0 + blockIdx.y;
+    if (jt > (int)blockIdx.x) return;
     __shared__ dd xi[TS][TS + 1];
     __shared__ dd xj[TS][TS + 1];
     const int r = threadIdx.x, c = threadIdx.y;
-    const int base = k0 + w, i0 = base + blockIdx.x * TS, j0 = base + blockIdx.y * TS;
+    const int base = k0 + w, i0 = base + blockIdx.x * TS, j0 = base + jt * TS;
     // thread (r, c) loads column c of the panel for row r of both tiles
     if (c < w) {
         xi[r][c] = (i0 + r < n) ? A[(size_t)(k0 + c) * n + i0 + r] : dd_make(0.0);
@@ -583,7 +587,12 @@ int32_t lrn_dd_create(lrn_dd_handle_t* out, int64_t n_var, int64_t nlin, int32_t
         cudaDeviceProp prop;
         LRN_CUDA(cudaGetDeviceProperties(&prop, h->device));
         LRN_REQUIRE(prop.major == 10, "libloraine_b200 is built for sm_100a only");
-        LRN_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        LRN_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        LRN_CUDA(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, prio_hi));
+        LRN_CUDA(cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, prio_lo));
+        LRN_CUDA(cudaEventCreateWithFlags(&h->evP, cudaEventDisableTiming));
+        LRN_CUDA(cudaEventCreateWithFlags(&h->evR, cudaEventDisableTiming));
         LRN_CUDA(cudaEventCreate(&h->ev0));
         LRN_CUDA(cudaEventCreate(&h->ev1));
         h->n = (int)n_var;
@@ -616,6 +625,9 @@ int32_t lrn_dd_destroy(lrn_dd_handle_t h) {
     if (!h) return LRN_OK;
     cudaSetDevice(h->device);
     if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
+    if (h->st2) { cudaStreamSynchronize(h->st2); cudaStreamDestroy(h->st2); }
+    if (h->evP) cudaEventDestroy(h->evP);
+    if (h->evR) cudaEventDestroy(h->evR);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -781,6 +793,10 @@ int32_t lrn_dd_schur_factor(lrn_dd_handle_t h) {
             const int n = h->n;
             LRN_CUDA(cudaMemcpyAsync(h->L.p, h->H.p, (size_t)n * n * sizeof(dd), cudaMemcpyDeviceToDevice, h->st));
             LRN_CUDA(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->st));
+            // One-step look-ahead on two streams: the panel chain (diagonal tile, tiles below it, update of the NEXT tile
+            // column) runs on h->st (high priority), the update of the rest of the trailing matrix on h->st2.  Both update
+            // kernels of consecutive steps touch the same tiles, so the chain waits for rest(k-1) before col(k).
+            bool rest_pending = false;
             for (int k0 = 0; k0 < n; k0 += TS) {
                 const int w = std::min(TS, n - k0);
                 k_dd_potrf_tile<<<1, dim3(TS, TS), 0, h->st>>>(h->L.p, n, k0, w, h->info.p, h->rdiag.p);
@@ -790,9 +806,20 @@ int32_t lrn_dd_schur_factor(lrn_dd_handle_t h) {
                 const unsigned nt = (unsigned)cdiv(below, TS);
                 k_dd_trsm_tile<<<nt, TS, 0, h->st>>>(h->L.p, n, k0, w, h->rdiag.p);
                 LRN_CHECK_LAUNCH();
-                k_dd_syrk_tile<<<dim3(nt, nt), dim3(TS, TS), 0, h->st>>>(h->L.p, n, k0, w);
+                if (rest_pending) LRN_CUDA(cudaStreamWaitEvent(h->st, h->evR, 0));       // rest(k-1) before col(k)
+                rest_pending = false;
+                if (nt > 1) {
+                    LRN_CUDA(cudaEventRecord(h->evP, h->st));
+                    LRN_CUDA(cudaStreamWaitEvent(h->st2, h->evP, 0));
+                    k_dd_syrk_tile<<<dim3(nt, nt - 1), dim3(TS, TS), 0, h->st2>>>(h->L.p, n, k0, w, 1);
+                    LRN_CHECK_LAUNCH();
+                    LRN_CUDA(cudaEventRecord(h->evR, h->st2));
+                    rest_pending = true;
+                }
+                k_dd_syrk_tile<<<dim3(nt, 1), dim3(TS, TS), 0, h->st>>>(h->L.p, n, k0, w, 0);
                 LRN_CHECK_LAUNCH();
             }
+            if (rest_pending) LRN_CUDA(cudaStreamWaitEvent(h->st, h->evR, 0));
             LRN_CUDA(cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
             LRN_CUDA(cudaStreamSynchronize(h->st));
         }

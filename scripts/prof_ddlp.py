@@ -1,5 +1,5 @@
 """Double-double LP path: device time per phase on a synthetic LP (default n = 2000 multipliers, 5000 LP rows) and the rate of
-the double-double Cholesky in dd multiply-adds per second (n^3/3 of them).
+the double-double Cholesky in dd multiply-adds per second (n^3/6 of them).
 usage: python scripts/prof_ddlp.py [n] [nlin] [density] [iterations]"""
 import os
 import sys
@@ -29,7 +29,7 @@ for it in range(iters):
     s.itertime = time.perf_counter() - t0
     dd_lp.check_convergence(s)
     t = s.timers()
-    fma = n ** 3 / 3
+    fma = n ** 3 / 6
     print("it %d: %.1f ms wall | assemble %.2f  factor %.2f (%.1f G dd-FMA/s)  solve %.2f  other %.2f ms | DIMACS %.3e" % (
         s.iter, s.itertime * 1e3, t["schur_assemble"], t["schur_factor"], fma / (t["schur_factor"] * 1e-3) / 1e9, t["schur_solve"],
         t["other"], float(s.DIMACS_error)), flush=True)
