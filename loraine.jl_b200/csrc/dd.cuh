@@ -111,6 +111,15 @@ DD_FN dd dd_sqrt(dd a) {
     return dd_add_d(dd_make(ax), DD_MUL(rem.hi, DD_MUL(x, 0.5)));
 }
 
+// 1/sqrt(a): one Newton step in double-double from the double estimate x: x + x (1 - a x^2) / 2; a > 0.  (The Cholesky tile
+// kernel needs both sqrt(a) = a * rsqrt(a) and its reciprocal: one rsqrt is ~1/3 of a sqrt followed by a division.)
+DD_FN dd dd_rsqrt(dd a) {
+    const double x = DD_DIV(1.0, DD_SQRT(a.hi));
+    const dd ax2 = dd_mul(a, two_prod(x, x));
+    const dd e = dd_sub(dd_make(1.0), ax2);
+    return dd_add(dd_make(x), dd_mul_d(e, DD_MUL(x, 0.5)));
+}
+
 DD_FN bool dd_lt(dd a, dd b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
 DD_FN bool dd_gt(dd a, dd b) { return dd_lt(b, a); }
 DD_FN bool dd_le_zero(dd a) { return !(a.hi > 0.0 || (a.hi == 0.0 && a.lo > 0.0)); }

@@ -20,8 +20,8 @@ int main() {
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> u(-1.0, 1.0);
     std::uniform_int_distribution<int> ex(-40, 40);
-    double worst[6] = {0, 0, 0, 0, 0, 0};
-    const char* name[6] = {"add", "sub", "mul", "div", "sqrt", "fma"};
+    double worst[7] = {0, 0, 0, 0, 0, 0, 0};
+    const char* name[7] = {"add", "sub", "mul", "div", "sqrt", "fma", "rsqrt"};
     for (int t = 0; t < 2000000; t++) {
         auto rnd = [&]() {
             const double hi = std::ldexp(u(rng), ex(rng));
@@ -38,11 +38,12 @@ int main() {
         if (b.hi != 0.0) { e = relerr(lrn::dd_div(a, b), qa / qb); if (e > worst[3]) worst[3] = e; }
         const dd p = lrn::dd_abs(a);
         e = relerr(lrn::dd_sqrt(p), sqrtq(val(p))); if (e > worst[4]) worst[4] = e;
+        if (val(p) > 0) { e = relerr(lrn::dd_rsqrt(p), 1 / sqrtq(val(p))); if (e > worst[6]) worst[6] = e; }
         e = (double)fabsq((val(lrn::dd_fma(a, b, c)) - (qa * qb + qc)) / (fabsq(qa * qb) + fabsq(qc))); if (e > worst[5]) worst[5] = e;
     }
     int bad = 0;
     const double tol = 0x1p-100;      // 2^-100 ~ 7.9e-31 (double-double: ~2^-104 per operation, a few ulps for div / sqrt)
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 7; k++) {
         printf("%s %.3e\n", name[k], worst[k]);
         if (!(worst[k] <= tol)) bad++;
     }
