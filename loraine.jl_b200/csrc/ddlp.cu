@@ -126,45 +126,49 @@ __global__ void __launch_bounds__(TS * TS) k_dd_potrf_tile(dd* __restrict__ A, i
     if (r < w && c < w) A[(size_t)(k0 + c) * n + k0 + r] = (r >= c) ? t[r][c] : dd_make(0.0);
 }
 
-// X Lkk' = A for the 32-row tile `blockIdx.x` below the diagonal tile: one warp, lane = row of the tile
-__global__ void __launch_bounds__(TS) k_dd_trsm_tile(dd* __restrict__ A, int n, int k0, int w, const dd* __restrict__ rdiag) {
+// X Lkk' = A for the 32-row tile `blockIdx.x` below the diagonal tile.  Eight warps per tile, lane = row of the tile.  The 32
+// columns are solved in four blocks of eight: first all warps subtract the contribution of the finished blocks from the eight
+// columns of the current block (warp = column: independent dot products), then warp 0 runs the short substitution inside the
+// block.  The dependent chain per row is 4 x 28 multiply-adds instead of 496 (a single warp doing the whole substitution took
+// 41 us per step at n = 2000 and was the longest kernel of the panel chain).
+constexpr int TRSM_CB = 8;
+__global__ void __launch_bounds__(TS * TRSM_CB) k_dd_trsm_tile(dd* __restrict__ A, int n, int k0, int w, const dd* __restrict__ rdiag) {
     __shared__ dd l[TS][TS + 1];
     __shared__ dd xr[TS][TS + 1];
     __shared__ dd rd[TS];
-    const int lane = threadIdx.x;
-    if (lane < w) rd[lane] = rdiag[k0 + lane];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = k0 + w + blockIdx.x * TS, row = i0 + lane;
-    for (int c = 0; c < w; c++) {
+    if (warp == 0 && lane < w) rd[lane] = rdiag[k0 + lane];
+    for (int c = warp; c < w; c += TRSM_CB) {
         if (lane < w) l[lane][c] = A[(size_t)(k0 + c) * n + k0 + lane];
-        if (row < n) xr[lane][c] = A[(size_t)(k0 + c) * n + row];
+        xr[lane][c] = (row < n) ? A[(size_t)(k0 + c) * n + row] : dd_make(0.0);
     }
-    __syncwarp();
-    if (row < n) {
-        for (int c = 0; c < w; c++) {
-            // eight independent partial sums: a double-double multiply-add is a ~25-deep dependent chain
+    __syncthreads();
+    for (int c0 = 0; c0 < w; c0 += TRSM_CB) {
+        const int c = c0 + warp;
+        if (c0 > 0 && c < w) {
             dd a0 = xr[lane][c], a1 = dd_make(0.0), a2 = dd_make(0.0), a3 = dd_make(0.0);
-            dd a4 = dd_make(0.0), a5 = dd_make(0.0), a6 = dd_make(0.0), a7 = dd_make(0.0);
-            int p = 0;
-            for (; p + 8 <= c; p += 8) {
+            for (int p = 0; p < c0; p += 4) {                       // c0 is a multiple of 8
                 a0 = dd_fms(xr[lane][p], l[c][p], a0);
                 a1 = dd_fms(xr[lane][p + 1], l[c][p + 1], a1);
                 a2 = dd_fms(xr[lane][p + 2], l[c][p + 2], a2);
                 a3 = dd_fms(xr[lane][p + 3], l[c][p + 3], a3);
-                a4 = dd_fms(xr[lane][p + 4], l[c][p + 4], a4);
-                a5 = dd_fms(xr[lane][p + 5], l[c][p + 5], a5);
-                a6 = dd_fms(xr[lane][p + 6], l[c][p + 6], a6);
-                a7 = dd_fms(xr[lane][p + 7], l[c][p + 7], a7);
             }
-            for (; p + 2 <= c; p += 2) {
-                a0 = dd_fms(xr[lane][p], l[c][p], a0);
-                a1 = dd_fms(xr[lane][p + 1], l[c][p + 1], a1);
-            }
-            for (; p < c; p++) a0 = dd_fms(xr[lane][p], l[c][p], a0);
-            const dd v = dd_add(dd_add(dd_add(a0, a1), dd_add(a2, a3)), dd_add(dd_add(a4, a5), dd_add(a6, a7)));
-            xr[lane][c] = dd_mul(v, rd[c]);
+            xr[lane][c] = dd_add(dd_add(a0, a1), dd_add(a2, a3));
         }
-        for (int c = 0; c < w; c++) A[(size_t)(k0 + c) * n + row] = xr[lane][c];
+        __syncthreads();
+        if (warp == 0) {
+            const int c1 = min(w, c0 + TRSM_CB);
+            for (int cc = c0; cc < c1; cc++) {
+                dd v = xr[lane][cc];
+                for (int p = c0; p < cc; p++) v = dd_fms(xr[lane][p], l[cc][p], v);
+                xr[lane][cc] = dd_mul(v, rd[cc]);
+            }
+        }
+        __syncthreads();
     }
+    if (row < n)
+        for (int c = warp; c < w; c += TRSM_CB) A[(size_t)(k0 + c) * n + row] = xr[lane][c];
 }
 
 // A(I, J) -= X_I X_J' for the tile pairs I >= J of the trailing matrix (K = w)
@@ -282,6 +286,8 @@ __device__ __forceinline__ dd dd_ldcg(const dd* p) {
 __global__ void __launch_bounds__(TRSV_T) k_dd_trsv_multi(const dd* __restrict__ L, const dd* __restrict__ rdiag, int n, dd* x,
                                                          int* flags, int epoch, int backward, int* err) {
     __shared__ dd part[TRSV_T / 32][TS];
+    __shared__ dd dt[TS][TS + 1];
+    __shared__ dd rds[TS];
     __shared__ int failed;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = TRSV_T / 32;
     const int nt = (n + TS - 1) / TS, G = gridDim.x;
@@ -290,37 +296,35 @@ __global__ void __launch_bounds__(TRSV_T) k_dd_trsv_multi(const dd* __restrict__
     for (int seq = blockIdx.x; seq < nt; seq += G) {
         const int i = backward ? nt - 1 - seq : seq;
         const int r0 = i * TS, w = min(TS, n - r0);
+        // the diagonal tile and its pivot reciprocals go to shared memory now: the 32 dependent steps of the tile solve below
+        // must not wait for global memory
+        for (int idx = tid; idx < TS * TS; idx += TRSV_T) {
+            const int r = idx & 31, c = idx >> 5;
+            dt[r][c] = (r < w && c < w) ? L[(size_t)(r0 + c) * n + r0 + r] : dd_make(0.0);
+        }
+        if (tid < TS) rds[tid] = (tid < w) ? rdiag[r0 + tid] : dd_make(0.0);
         // ---- products with the tiles this one depends on: forward k < i (lane = row of tile i), backward k > i (lane = column) ----
         dd a0 = dd_make(0.0), a1 = dd_make(0.0), a2 = dd_make(0.0), a3 = dd_make(0.0);
         const int ndep = backward ? nt - 1 - i : i;
         for (int q = warp; q < ndep; q += nw) {
             const int k = backward ? nt - 1 - q : q;           // dependencies in the order they are published
-            bool ok = true;
-            if (lane == 0) ok = dd_wait_flag(flags + k, epoch, err);
-            ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-            if (!ok) { failed = 1; break; }
             const int c0 = k * TS, wk = min(TS, n - c0);
-            if (lane < w) {
-                if (!backward) {
-                    const dd* Lp = L + (size_t)c0 * n + r0 + lane;             // L[r0 + lane, c0 + c]
+            {
+                bool ok = true;
+                if (lane == 0) ok = dd_wait_flag(flags + k, epoch, err);
+                ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+                if (!ok) { failed = 1; break; }
+                if (lane < w) {
+                    const dd* Lp = backward ? L + (size_t)(r0 + lane) * n + c0 : L + (size_t)c0 * n + r0 + lane;
+                    const size_t step = backward ? 1 : (size_t)n;
                     int c = 0;
                     for (; c + 4 <= wk; c += 4) {
-                        a0 = dd_fma(Lp[(size_t)c * n], dd_ldcg(x + c0 + c), a0);
-                        a1 = dd_fma(Lp[(size_t)(c + 1) * n], dd_ldcg(x + c0 + c + 1), a1);
-                        a2 = dd_fma(Lp[(size_t)(c + 2) * n], dd_ldcg(x + c0 + c + 2), a2);
-                        a3 = dd_fma(Lp[(size_t)(c + 3) * n], dd_ldcg(x + c0 + c + 3), a3);
+                        a0 = dd_fma(Lp[(size_t)c * step], dd_ldcg(x + c0 + c), a0);
+                        a1 = dd_fma(Lp[(size_t)(c + 1) * step], dd_ldcg(x + c0 + c + 1), a1);
+                        a2 = dd_fma(Lp[(size_t)(c + 2) * step], dd_ldcg(x + c0 + c + 2), a2);
+                        a3 = dd_fma(Lp[(size_t)(c + 3) * step], dd_ldcg(x + c0 + c + 3), a3);
                     }
-                    for (; c < wk; c++) a0 = dd_fma(Lp[(size_t)c * n], dd_ldcg(x + c0 + c), a0);
-                } else {
-                    const dd* Lp = L + (size_t)(r0 + lane) * n + c0;           // L'[r0 + lane, c0 + c] = L[c0 + c, r0 + lane]
-                    int c = 0;
-                    for (; c + 4 <= wk; c += 4) {
-                        a0 = dd_fma(Lp[c], dd_ldcg(x + c0 + c), a0);
-                        a1 = dd_fma(Lp[c + 1], dd_ldcg(x + c0 + c + 1), a1);
-                        a2 = dd_fma(Lp[c + 2], dd_ldcg(x + c0 + c + 2), a2);
-                        a3 = dd_fma(Lp[c + 3], dd_ldcg(x + c0 + c + 3), a3);
-                    }
-                    for (; c < wk; c++) a0 = dd_fma(Lp[c], dd_ldcg(x + c0 + c), a0);
+                    for (; c < wk; c++) a0 = dd_fma(Lp[(size_t)c * step], dd_ldcg(x + c0 + c), a0);
                 }
             }
         }
@@ -338,18 +342,18 @@ __global__ void __launch_bounds__(TRSV_T) k_dd_trsv_multi(const dd* __restrict__
             if (!backward) {
                 for (int c = 0; c < w; c++) {
                     dd xc = dd_make(0.0);
-                    if (lane == c) xc = dd_mul(v, rdiag[r0 + c]);
+                    if (lane == c) xc = dd_mul(v, rds[c]);
                     xc = dd_shfl(xc, c);
                     if (lane == c) v = xc;
-                    else if (lane > c && lane < w) v = dd_fms(L[(size_t)(r0 + c) * n + r0 + lane], xc, v);
+                    else if (lane > c && lane < w) v = dd_fms(dt[lane][c], xc, v);
                 }
             } else {
                 for (int c = w - 1; c >= 0; c--) {
                     dd xc = dd_make(0.0);
-                    if (lane == c) xc = dd_mul(v, rdiag[r0 + c]);
+                    if (lane == c) xc = dd_mul(v, rds[c]);
                     xc = dd_shfl(xc, c);
                     if (lane == c) v = xc;
-                    else if (lane < c) v = dd_fms(L[(size_t)(r0 + lane) * n + r0 + c], xc, v);
+                    else if (lane < c) v = dd_fms(dt[c][lane], xc, v);          // L'[lane, c] = L[c, lane]
                 }
             }
             if (lane < w) x[r0 + lane] = v;
@@ -817,7 +821,7 @@ int32_t lrn_dd_schur_factor(lrn_dd_handle_t h) {
                     const int below = n - k0 - w;
                     if (below <= 0) break;
                     const unsigned nt = (unsigned)cdiv(below, TS);
-                    k_dd_trsm_tile<<<nt, TS, 0, h->st>>>(h->L.p, n, k0, w, h->rdiag.p);
+                    k_dd_trsm_tile<<<nt, TS * TRSM_CB, 0, h->st>>>(h->L.p, n, k0, w, h->rdiag.p);
                     LRN_CHECK_LAUNCH();
                     if (rest_pending) LRN_CUDA(cudaStreamWaitEvent(h->st, h->evR, 0));       // rest(k-1) before col(k)
                     rest_pending = false;
