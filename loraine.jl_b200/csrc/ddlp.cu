@@ -4,8 +4,9 @@
 //   residuals        src/predictor_corrector.jl:8-22        Schur matrix   :36-39        right-hand sides :43-50, :183-192
 //   Cholesky + solve :57-90, :199                             find_step_lin  :329-364      sigma trace      :163-166
 //   find_mu          src/Solvers.jl:480-494                   DIMACS errors  :496-523
-// Everything below is plain CUDA-core arithmetic on (hi, lo) pairs (dd.cuh): a double-double multiply-add is ~25 dependent
-// FP64 operations, so these kernels are bound by FP64 issue, not by memory.  Layout: vectors as arrays of dd (16 B per
+// Everything below is plain CUDA-core arithmetic on (hi, lo) pairs (dd.cuh): a double-double multiply-add is 28 FP64
+// instructions (24 DADD + 2 DMUL + 2 DFMA), most of them dependent, so these kernels are bound by FP64 issue (the trailing
+// update runs the FP64 pipe at 89 %, profiles/r2_dd_syrk_ncu_full.csv) or by dependent-issue latency, not by memory.  Layout: vectors as arrays of dd (16 B per
 // entry, one 128-bit access), H and L dense column-major with leading dimension n.
 #include "common.cuh"
 #include "dd.cuh"
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(TS * TS) k_dd_syrk_tile(dd* __restrict__ A, in
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// triangular solves with the dd factor: one CTA of 1024 threads, 32 unknowns per step
+// triangular solves with the dd factor, 32 unknowns per step.  One CTA of 1024 threads for n <= 64; k_dd_trsv_multi otherwise
 // ------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_dd_trsv_fwd(const dd* __restrict__ L, const dd* __restrict__ rdiag, int n, dd* __restrict__ x) {
     __shared__ dd xt[TS];
