@@ -665,6 +665,9 @@ int32_t lrn_dd_set_lin(lrn_dd_handle_t h, const int64_t* colptr, const int64_t* 
             LRN_REQUIRE(colptr[k] >= 1 && colptr[k] - 1 <= nnz && (k == 0 || colptr[k] >= colptr[k - 1]), "colptr not monotone");
             cp[k] = (int)(colptr[k] - 1);
         }
+        for (int k = 0; k < m; k++)      // the Schur kernel updates the entries of one column in parallel: no duplicates allowed
+            for (int e = cp[k] + 1; e < cp[k + 1]; e++)
+                LRN_REQUIRE(rowval[e] > rowval[e - 1], "row indices of a column must be strictly increasing (sorted, no duplicates)");
         for (long long e = 0; e < nnz; e++) {
             LRN_REQUIRE(rowval[e] >= 1 && rowval[e] <= n, "row index out of range");
             ci[e] = (int)(rowval[e] - 1);
