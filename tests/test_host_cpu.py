@@ -230,3 +230,133 @@ def test_plain_c_host_compiles_against_the_header_only(pkg, tmp_path):
         M.write_sdpa(path, int(z["n"]), [int(b) for b in z["bs"]], z["c"], z["body"])
         r = subprocess.run([exe, path], capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def _c_prototypes():
+    """{entry point: number of parameters} from the three headers."""
+    protos = {}
+    for header in ("loraine_b200.h", "loraine_b200_debug.h", "loraine_b200_dd.h"):
+        txt = open(os.path.join(ROOT, "include", header)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b(lrn_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+            args = m.group(2).strip()
+            protos[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return protos
+
+
+def _c_param_types():
+    """{entry point: [Julia ccall types each C parameter may be bound to]}"""
+    def julia_types(decl):
+        d = " ".join(decl.replace("const", " ").split())
+        is_array = "[" in d
+        d = re.sub(r"\[[0-9]*\]", "", d)
+        stars = d.count("*")
+        base = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", d.replace("*", " ")).strip() or d.replace("*", " ").strip()
+        base = base.split()[0]
+        if is_array:
+            stars += 1
+        prim = {"int32_t": "Int32", "int64_t": "Int64", "double": "Float64"}
+        if base in ("lrn_handle_t", "lrn_dd_handle_t"):
+            return ["Ptr{Cvoid}"] if stars == 0 else ["Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"]
+        if base == "lrn_options_t":
+            return ["Ref{Options}", "Ptr{Options}"]
+        if base == "char":
+            return ["Cstring", "Ptr{UInt8}"]
+        if base == "void":
+            return ["Ptr{Cvoid}", "Ptr{UInt8}"]
+        j = prim[base]
+        if stars == 0:
+            return [j]
+        if stars == 1:
+            return [f"Ptr{{{j}}}", f"Ref{{{j}}}"]
+        return [f"Ptr{{Ptr{{{j}}}}}"]
+    out = {}
+    for header in ("loraine_b200.h", "loraine_b200_debug.h", "loraine_b200_dd.h"):
+        txt = open(os.path.join(ROOT, "include", header)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b(lrn_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+            args = m.group(2).strip()
+            out[m.group(1)] = [] if args in ("", "void") else [julia_types(a.strip()) for a in args.split(",")]
+    return out
+
+
+def _julia_ccalls(path):
+    """[(entry point, number of argument types, number of arguments)] of every ccall in a Julia source file."""
+    src = open(path).read()
+    out = []
+    for m in re.finditer(r"ccall\(\(:(lrn_[A-Za-z0-9_]+),\s*LIB\[\]\),", src):
+        i = m.end()
+        depth, j, parts, cur = 1, i, [], ""
+        while depth > 0:                      # split the rest of the ccall(...) at top-level commas
+            ch = src[j]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    break
+            if ch == "," and depth == 1:
+                parts.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+            j += 1
+        parts.append(cur.strip())
+        ret, types, args = parts[0], parts[1], parts[2:]
+        assert types.startswith("(") and types.endswith(")"), (m.group(1), types)
+        inner = types[1:-1].strip()
+        # split the type tuple at its top-level commas (Ref{Ptr{Cvoid}} contains braces, not commas, but be safe)
+        tparts, d, cur = [], 0, ""
+        for ch in inner:
+            if ch in "({[":
+                d += 1
+            elif ch in ")}]":
+                d -= 1
+            if ch == "," and d == 0:
+                tparts.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            tparts.append(cur.strip())
+        nargs = len([a for a in args if a != ""])
+        if any(a.endswith("...") for a in args):           # csc(A)... splats three arrays
+            nargs += 2 * sum(1 for a in args if a.endswith("..."))
+        out.append((m.group(1), ret, len(tparts), nargs, tparts))
+    return out
+
+
+@pytest.mark.parametrize("fname", ["LoraineB200.jl", "LoraineB200DD.jl"])
+def test_julia_ccalls_match_the_headers(fname):
+    """The Julia shims cannot be executed here (no Julia): at least every ccall must name an exported entry point with the
+    header's number of parameters, pass as many arguments as it declares types, and use the header's return type."""
+    protos = _c_prototypes()
+    calls = _julia_ccalls(os.path.join(ROOT, "julia", fname))
+    assert len(calls) >= 15
+    ctypes_ = _c_param_types()
+    for name, ret, ntypes, nargs, jtypes in calls:
+        assert name in protos, name
+        assert ntypes == protos[name], (name, ntypes, protos[name])
+        assert nargs == ntypes, (name, nargs, ntypes)
+        for k, (jt, allowed) in enumerate(zip(jtypes, ctypes_[name])):          # Int32 vs Int64, Float64 vs pointer, ...
+            assert jt in allowed, (name, k, jt, allowed)
+        want = "Cstring" if name.endswith("last_error") else ("Int64" if name == "lrn_kernel_launches" else "Int32")
+        assert ret == want, (name, ret)
+
+
+def test_options_struct_layout_is_the_same_in_c_python_and_julia(pkg):
+    """lrn_options_t (include/loraine_b200.h) = _lib.lrn_options_t (ctypes) = struct Options (julia/LoraineB200.jl): same
+    fields, order and widths -- the struct crosses the boundary by pointer."""
+    import ctypes as C
+    from loraine_jl_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "loraine_b200.h")).read()
+    body = re.search(r"typedef struct lrn_options \{(.*?)\} lrn_options_t;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = [(m.group(2), m.group(1)) for m in re.finditer(r"\b(int32_t|double)\s+(\w+)\s*;", body)]
+    py_fields = [(n, {C.c_int32: "int32_t", C.c_double: "double"}[t]) for n, t in _lib.lrn_options_t._fields_]
+    assert c_fields == py_fields
+    jl = open(os.path.join(ROOT, "julia", "LoraineB200.jl")).read()
+    jbody = re.search(r"struct Options[^\n]*\n(.*?)\nend", jl, flags=re.S).group(1)
+    j_fields = [(m.group(1), {"Int32": "int32_t", "Float64": "double"}[m.group(2)]) for m in re.finditer(r"(\w+)::(Int32|Float64)", jbody)]
+    assert j_fields == c_fields
+    assert C.sizeof(_lib.lrn_options_t) == 8 * 4 + 2 * 8 + 2 * 4
