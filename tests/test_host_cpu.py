@@ -360,3 +360,29 @@ def test_options_struct_layout_is_the_same_in_c_python_and_julia(pkg):
     j_fields = [(m.group(1), {"Int32": "int32_t", "Float64": "double"}[m.group(2)]) for m in re.finditer(r"(\w+)::(Int32|Float64)", jbody)]
     assert j_fields == c_fields
     assert C.sizeof(_lib.lrn_options_t) == 8 * 4 + 2 * 8 + 2 * 4
+
+
+@pytest.mark.parametrize("fname", ["LoraineB200.jl", "LoraineB200DD.jl"])
+def test_julia_shim_overrides_existing_reference_methods(fname):
+    """Every `function S.name(...)` of the shims must be a method of a function the reference defines in module Solvers with the
+    same number of positional arguments, and every `invoke(S.name, Tuple{...}, ...)` must name as many types.  Reads the
+    reference sources: skipped where /root/reference does not exist (the GPU box)."""
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference sources not present")
+    defs = {}
+    for f in ("Solvers.jl", "predictor_corrector.jl", "prepare_W.jl", "initial_point.jl"):
+        for m in re.finditer(r"^function\s+(\w+)\(([^)]*)\)", open(os.path.join(ref, f)).read(), flags=re.M):
+            args = [a for a in m.group(2).split(";")[0].split(",") if a.strip()]
+            defs.setdefault(m.group(1), set()).add(len(args))
+    src = open(os.path.join(ROOT, "julia", fname)).read()
+    overrides = re.findall(r"^function S\.(\w+)\(([^)]*)\)", src, flags=re.M)
+    assert len(overrides) >= 10
+    for name, args in overrides:
+        n = len([a for a in args.split(",") if a.strip()])
+        assert name in defs, name
+        assert n in defs[name], (name, n, defs[name])
+    for m in re.finditer(r"invoke\(S\.(\w+),\s*Tuple\{([^}]*(?:\{[^}]*\})?[^}]*)\}", src):
+        name = m.group(1)
+        ntypes = len([t for t in re.sub(r"\{[^}]*\}", "", m.group(2)).split(",") if t.strip()])
+        assert name in defs and ntypes in defs[name], (name, ntypes, defs.get(name))
