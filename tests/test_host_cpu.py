@@ -386,3 +386,28 @@ def test_julia_shim_overrides_existing_reference_methods(fname):
         name = m.group(1)
         ntypes = len([t for t in re.sub(r"\{[^}]*\}", "", m.group(2)).split(",") if t.strip()])
         assert name in defs and ntypes in defs[name], (name, ntypes, defs.get(name))
+
+
+@pytest.mark.parametrize("fname", ["LoraineB200.jl", "LoraineB200DD.jl"])
+def test_julia_shim_uses_existing_solver_and_model_fields(fname):
+    """Every `solver.field` / `md.field` the shims touch must be a field of the reference's MySolver / MyModel structs
+    (src/Solvers.jl:18-107, src/model.jl:34-60).  Skipped where /root/reference does not exist."""
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference sources not present")
+
+    def struct_fields(path, name):
+        txt = open(path).read()
+        body = re.search(r"mutable struct " + name + r"[^\n]*\n(.*?)\n\s*function ", txt, flags=re.S).group(1)
+        return {m.group(1) for m in re.finditer(r"^\s*(\w+)(?:::[^\n]*)?\s*(?:#.*)?$", body, flags=re.M) if m.group(1) not in ("end",)}
+
+    solver_fields = struct_fields(os.path.join(ref, "Solvers.jl"), "MySolver")
+    model_fields = struct_fields(os.path.join(ref, "model.jl"), "MyModel")
+    assert {"X", "S", "y", "cholBBBB", "regcount", "alpha_lin", "mu", "sigma", "itertime"} <= solver_fields
+    assert {"AA", "C", "b", "C_lin", "d_lin", "nlmi", "nlin", "msizes", "n"} <= model_fields
+    src = open(os.path.join(ROOT, "julia", fname)).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    used_s = set(re.findall(r"\bsolver\.(\w+)", src))
+    used_m = set(re.findall(r"\bmd\.(\w+)", src))
+    assert used_s and used_s <= solver_fields, sorted(used_s - solver_fields)
+    assert used_m <= model_fields, sorted(used_m - model_fields)
