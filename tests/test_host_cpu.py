@@ -411,3 +411,35 @@ def test_julia_shim_uses_existing_solver_and_model_fields(fname):
     used_m = set(re.findall(r"\bmd\.(\w+)", src))
     assert used_s and used_s <= solver_fields, sorted(used_s - solver_fields)
     assert used_m <= model_fields, sorted(used_m - model_fields)
+
+
+def _julia_block_balance(src):
+    """(number of block openers, number of `end`s, final bracket depth) of a Julia source, ignoring strings, comments, and
+    the `for` / `if` of comprehensions and the `end` of indexing (both live inside brackets)."""
+    src = re.sub(r'"""(?:.|\n)*?"""', '""', src)
+    src = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', src)
+    src = re.sub(r"#[^\n]*", "", src)
+    src = re.sub(r"'(?:\\.|[^'\\\n])'", "' '", src)
+    tokens = re.findall(r"[A-Za-z_]\w*|[()\[\]{}]|\S", src)
+    openers = {"function", "if", "for", "while", "begin", "struct", "module", "try", "let", "do", "quote", "macro"}
+    depth = opened = closed = 0
+    prev = ""
+    for t in tokens:
+        if t in "([{":
+            depth += 1
+        elif t in ")]}":
+            depth -= 1
+        elif depth == 0 and t in openers and prev != ":" and prev != ".":      # not the symbol :if / a field .begin
+            opened += 1
+        elif depth == 0 and t == "end" and prev != ":":
+            closed += 1
+        prev = t
+    return opened, closed, depth
+
+
+@pytest.mark.parametrize("fname", ["LoraineB200.jl", "LoraineB200DD.jl"])
+def test_julia_shim_blocks_are_balanced(fname):
+    """No Julia parser here: at least brackets close and every block opener has its `end`."""
+    opened, closed, depth = _julia_block_balance(open(os.path.join(ROOT, "julia", fname)).read())
+    assert depth == 0
+    assert opened == closed and opened > 20, (opened, closed)
